@@ -1,0 +1,153 @@
+/*
+ * strkit_b200.h -- C ABI of the B200-native replacement for STRkit's per-read repeat-count
+ * hot path.  Plain C: pointers, sizes, int status codes (0 = OK); no exceptions cross the
+ * boundary; strk_last_error() returns a thread-local message for the last non-zero status.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference checkout):
+ *
+ *   strk_count_reads / strk_batch_*   the per-read loop of call_locus (strkit/call/call_locus.py:
+ *                                     1079,1129-1161) around strkit.call.repeats.get_repeat_count
+ *                                     (strkit/call/repeats.py:47-70), i.e. the PyO3 binding
+ *                                     strkit_rust_ext.get_repeat_count(start_count, tr_seq, fl, fr,
+ *                                     motif, max_iters, local_search_range, step_size,
+ *                                     use_shortcuts=False) (repeats.py:58-68), batched over the
+ *                                     reads of many loci (replacing the worker pool's per-locus
+ *                                     calls, strkit/call/call_sample.py:103-157).
+ *   strk_score_tables                 the candidate scoring inside that search: the alignment of
+ *                                     fl + motif*n + fr against the profile of fl + tr + fr for a
+ *                                     whole window of n at once (parasail sg*_scan_profile_sat).
+ *   strk_ref_boundary_tables          score_ref_boundaries (repeats.py:23-43): the two
+ *                                     parasail.sg_qe_scan_profile_sat calls, for a window of n.
+ *   strk_ref_counts                   get_ref_repeat_count (repeats.py:73-192), batched over loci.
+ *   strk_init(matrix, gap...)         strkit/call/align_matrix.py:15-44 (dna_matrix, indel_penalty)
+ *                                     and parasail.profile_create_sat (repeats.py:92-93).
+ *
+ * Sequences are passed as they are in the reference: ASCII bytes (any case; IUPAC codes, the
+ * low-quality wildcard 'X', unknown bytes -> parasail's wildcard column).  The device encodes.
+ *
+ * Ownership: every buffer is caller-allocated and caller-freed; the library keeps no host
+ * pointer after a call returns.  Threading: one context per GPU per host thread; calls on one
+ * context are not re-entrant.  There is no CPU fallback: without a CUDA device strk_init fails.
+ */
+#ifndef STRKIT_B200_H
+#define STRKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct strk_ctx strk_ctx;
+typedef struct strk_batch strk_batch;
+
+/* status codes */
+#define STRK_OK 0
+#define STRK_ERR_ARG 1     /* invalid argument (null pointer, negative size, empty sequence, ...)  */
+#define STRK_ERR_CUDA 2    /* CUDA runtime error (message has the detail)                          */
+#define STRK_ERR_NOMEM 3   /* host or device allocation failed                                     */
+#define STRK_ERR_UNSUPPORTED 4 /* e.g. gap_open != gap_extend (the reference always passes 5, 5)   */
+#define STRK_ERR_SEARCH 5  /* the search scored nothing (reference raises ValueError)              */
+
+/* free-end flags of the semi-global alignment; s1 = db (the profiled sequence), s2 = candidate */
+#define STRK_S1_BEG_FREE 1
+#define STRK_S1_END_FREE 2
+#define STRK_S2_BEG_FREE 4
+#define STRK_S2_END_FREE 8
+#define STRK_MODE_SG 15   /* parasail "sg"    */
+#define STRK_MODE_SG_QE 2 /* parasail "sg_qe" */
+
+/* tie-break switches of the read-path search (0 = the in-tree Python semantics) */
+#define STRK_TIE_WINDOW_LAST 1
+#define STRK_TIE_FINAL_LAST 2
+
+#define STRK_NSYM 17
+
+/* kernel selection for strk_batch_run / strk_count_reads */
+#define STRK_KERNEL_AUTO 0    /* packed u16x2 kernel where its preconditions hold, else general */
+#define STRK_KERNEL_GENERAL 1 /* int32 general kernel for everything (any length / alphabet)    */
+
+const char *strk_last_error(void);
+const char *strk_version(void);
+
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int strk_device_count(void);
+
+/* Create a context on `device`.  matrix = 17x17 row-major substitution scores (align_matrix.py),
+ * end_flags = free ends of the read-path alignment (STRK_MODE_SG by default in the wrappers),
+ * tie_flags = STRK_TIE_* switches. */
+int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM], int gap_open, int gap_extend, int end_flags,
+              int tie_flags, strk_ctx **ctx);
+int strk_destroy(strk_ctx *ctx);
+
+/* Pin / unpin a caller-owned host buffer so that copies are asynchronous DMA. */
+int strk_host_register(void *ptr, uint64_t bytes);
+int strk_host_unregister(void *ptr);
+
+/*
+ * A batch = the reads of n_loci loci, in locus order and read order (the order matters: the start
+ * guess of read k uses the results of reads < k of the same locus, call_locus.py:1129-1161).
+ *   arena        ASCII bytes holding every sequence
+ *   seq_off[r]   offset of read r's concatenation fl + tr + fr (contiguous)
+ *   lens[3r..]   {len(fl), len(tr), len(fr)}
+ *   est_cn[r]    get_est_copy_num() of the read (call_locus.py:1129)
+ *   read_begin   n_loci + 1 prefix offsets into the read arrays
+ *   motif_off/motif_len  per locus, into the same arena
+ * strk_batch_upload copies everything to the device (H2D) and builds the work plan.
+ */
+int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                      const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, strk_batch **batch);
+
+/* Run the whole search for a resident batch: score tables (CUDA), exact replay of the reference's
+ * hill-climb per locus (CUDA), widening passes for reads whose search left the table window.
+ * Results stay on the device.  `stream` is a cudaStream_t (NULL = the context's own stream);
+ * the call returns after the work has completed (the widening check needs the status word). */
+int strk_batch_run(strk_ctx *ctx, strk_batch *batch, int max_iters, int local_search_range, int step_size,
+                   int kernel, void *stream);
+
+/* out[4r..4r+3] = {best_n, best_score, n_explored, start_count used}  (D2H). */
+int strk_batch_download(strk_ctx *ctx, strk_batch *batch, int32_t *out);
+int strk_batch_free(strk_ctx *ctx, strk_batch *batch);
+
+/* Convenience: upload + run + download with host buffers (the call the Python batcher makes). */
+int strk_count_reads(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                     const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                     const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, int max_iters,
+                     int local_search_range, int step_size, int kernel, int32_t *out);
+
+/* Raw score tables: scores[out_off[r] + (n - n_lo[r])] = alignment score of fl + motif*n + fr vs
+ * fl + tr + fr for n in [n_lo[r], n_hi[r]], read r using the motif of locus motif_idx[r]. */
+int strk_score_tables(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                      const int32_t *lens, const int32_t *motif_idx, const int32_t *n_lo, const int32_t *n_hi,
+                      int64_t n_reads, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_motifs,
+                      const uint64_t *out_off, int kernel, int32_t *scores);
+
+/* score_ref_boundaries for a window of n: out[4*(out_off[l] + n - n_lo[l]) ..] =
+ * {fwd_score, fwd_end_query, rev_score, rev_end_query}  (end_query as parasail reports it;
+ * r_adj = fwd_end_query + 1 - len(fl) - ref_size, repeats.py:34,41). */
+int strk_ref_boundary_tables(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                             const int32_t *lens, const int32_t *n_lo, const int32_t *n_hi, int64_t n_loci,
+                             const uint64_t *motif_off, const int32_t *motif_len, const uint64_t *out_off,
+                             int32_t *out);
+
+/* get_ref_repeat_count for n_loci loci.  start_count / ref_size / rc params per locus
+ * (rc_params[3l..] = {max_iters, local_search_range, step_size}, repeat_count_params.py:17-42).
+ * out[8l..] = {cn, score, l_offset, r_offset, n_offset_scores, n_iters_final, new_len_fl, new_len_fr}. */
+int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                    const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
+                    const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off, const int32_t *motif_len,
+                    int vcf_anchor_size, int respect_coords, int32_t *out);
+
+/* Counters of the last strk_batch_run on this context:
+ *   stats[0] executed DP cells (real cells, padding excluded)
+ *   stats[1] reference-equivalent DP cells (sum over the sizes the reference search scores)
+ *   stats[2] kernels launched           stats[3] DP-kernel time, ms (CUDA events on the run's stream)
+ *   stats[4] replay-kernel time, ms     stats[5] widening passes run
+ *   stats[6] reads handled by the packed kernel   stats[7] reads handled by the general kernel */
+int strk_get_stats(strk_ctx *ctx, double stats[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,102 @@
+"""Host-side batcher: packs the hot-path tuples of many loci into flat arenas for the device.
+
+Replaces the per-locus, per-read Python->Rust calls of the reference's worker pool
+(strkit/call/call_sample.py:103-157 -> call_locus.py:1082-1161 -> repeats.py:47-70): instead of one
+FFI call per read, the reads of a whole block of loci become ONE call across the C ABI.
+
+A tuple is exactly what the reference passes to get_repeat_count (call_locus.py:1148-1155):
+(start-count estimate, tr_seq_wc, flank_left_seq_wc[-flank:], flank_right_seq_wc[:flank], motif).
+Sequences stay ASCII (any case, IUPAC, 'X' wildcards); the device encodes them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Sequence
+
+import numpy as np
+
+__all__ = ["ReadBatch", "LocusReads", "pack_loci"]
+
+
+@dataclass
+class LocusReads:
+    """The reads of one locus, in the order the reference iterates them (call_locus.py:1082)."""
+    motif: str
+    est_cn: Sequence[int]          # get_est_copy_num() per read (call_locus.py:1129)
+    tr_seqs: Sequence[str]         # tr_seq_wc
+    flank_left_seqs: Sequence[str]
+    flank_right_seqs: Sequence[str]
+
+
+@dataclass
+class ReadBatch:
+    arena: np.ndarray        # uint8, ASCII
+    seq_off: np.ndarray      # uint64 [n_reads]   offset of fl + tr + fr
+    lens: np.ndarray         # int32  [n_reads, 3]
+    est_cn: np.ndarray       # int32  [n_reads]
+    read_begin: np.ndarray   # int64  [n_loci + 1]
+    motif_off: np.ndarray    # uint64 [n_loci]
+    motif_len: np.ndarray    # int32  [n_loci]
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.est_cn.shape[0])
+
+    @property
+    def n_loci(self) -> int:
+        return int(self.motif_len.shape[0])
+
+    def validate(self) -> None:
+        assert self.arena.dtype == np.uint8 and self.arena.flags.c_contiguous
+        assert self.seq_off.dtype == np.uint64 and self.lens.dtype == np.int32 and self.est_cn.dtype == np.int32
+        assert self.read_begin.dtype == np.int64 and self.motif_off.dtype == np.uint64
+        assert self.motif_len.dtype == np.int32
+        assert self.lens.shape == (self.n_reads, 3) and self.read_begin.shape == (self.n_loci + 1,)
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in (self.arena, self.seq_off, self.lens, self.est_cn, self.read_begin,
+                                          self.motif_off, self.motif_len)))
+
+    def slice_loci(self, lo: int, hi: int) -> "ReadBatch":
+        """Loci [lo, hi) as their own batch (shares the arena; offsets stay valid)."""
+        r0, r1 = int(self.read_begin[lo]), int(self.read_begin[hi])
+        return ReadBatch(self.arena, self.seq_off[r0:r1].copy(), self.lens[r0:r1].copy(), self.est_cn[r0:r1].copy(),
+                         (self.read_begin[lo:hi + 1] - r0).copy(), self.motif_off[lo:hi].copy(),
+                         self.motif_len[lo:hi].copy())
+
+
+def pack_loci(loci: Iterable[LocusReads]) -> ReadBatch:
+    """Pack per-locus string tuples into one arena.  One bytes.join for the sequences; the per-read Python
+    work is only the length bookkeeping (use strkit_b200.synth for fully vectorised synthetic batches)."""
+    chunks: list[bytes] = []
+    lens: list[tuple[int, int, int]] = []
+    est: list[int] = []
+    read_begin = [0]
+    motif_lens: list[int] = []
+    motifs: list[bytes] = []
+    for lr in loci:
+        n = len(lr.tr_seqs)
+        if not (len(lr.est_cn) == len(lr.flank_left_seqs) == len(lr.flank_right_seqs) == n):
+            raise ValueError("LocusReads: per-read sequences must have equal lengths")
+        for e, tr, fl, fr in zip(lr.est_cn, lr.tr_seqs, lr.flank_left_seqs, lr.flank_right_seqs):
+            chunks.append(fl.encode("ascii"))
+            chunks.append(tr.encode("ascii"))
+            chunks.append(fr.encode("ascii"))
+            lens.append((len(fl), len(tr), len(fr)))
+            est.append(int(e))
+        read_begin.append(len(est))
+        motifs.append(lr.motif.encode("ascii"))
+        motif_lens.append(len(lr.motif))
+    lens_a = np.asarray(lens, dtype=np.int32).reshape(-1, 3)
+    tot = lens_a.sum(axis=1, dtype=np.int64)
+    seq_off = np.zeros(len(est), dtype=np.uint64)
+    if len(est):
+        seq_off[1:] = np.cumsum(tot)[:-1]
+    seq_bytes = int(tot.sum())
+    motif_len = np.asarray(motif_lens, dtype=np.int32)
+    motif_off = np.zeros(len(motif_lens), dtype=np.uint64)
+    if len(motif_lens):
+        motif_off[:] = seq_bytes + np.concatenate([[0], np.cumsum(motif_len, dtype=np.int64)[:-1]])
+    arena = np.frombuffer(b"".join(chunks) + b"".join(motifs), dtype=np.uint8)
+    return ReadBatch(arena=arena, seq_off=seq_off, lens=lens_a, est_cn=np.asarray(est, dtype=np.int32),
+                     read_begin=np.asarray(read_begin, dtype=np.int64), motif_off=motif_off, motif_len=motif_len)

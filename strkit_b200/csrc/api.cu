@@ -1,0 +1,669 @@
+// api.cu -- C ABI (include/strkit_b200.h), context and batch management, launch orchestration.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/strkit_b200.h"
+#include "dp_general.cuh"
+#include "replay.cuh"
+#include "strk_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return set_err(STRK_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,            \
+                           cudaGetErrorString(e_));                                                       \
+    } while (0)
+
+extern "C" const char *strk_last_error(void) { return g_err; }
+extern "C" const char *strk_version(void) { return "strkit_b200 0.1 (sm_100a)"; }
+
+extern "C" int strk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device buffer that only grows
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 16;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct strk_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    ScoreConsts h_consts;
+    ScoreConsts *d_consts = nullptr;
+    int gap = 5, end_flags = STRK_MODE_SG, tie_flags = 0;
+    DevBuf<int> scratch;
+    DevBuf<FamDesc> fams;
+    DevBuf<int> table;
+    DevBuf<long long> table64;
+    DevBuf<int> list_a, list_b;      // widening-pass lists
+    DevBuf<long long> list_c;
+    unsigned int *d_queue = nullptr;  // [0] work queue, [1] miss counter
+    double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct strk_batch {
+    long long n_reads = 0, n_loci = 0;
+    unsigned char *d_arena = nullptr;
+    unsigned long long *d_seq_off = nullptr, *d_motif_off = nullptr;
+    int *d_lens = nullptr, *d_est = nullptr, *d_motif_len = nullptr, *d_read_locus = nullptr, *d_order = nullptr;
+    long long *d_read_begin = nullptr;
+    int *d_out = nullptr;
+    unsigned char *d_status = nullptr;
+    // host mirrors used for planning (scratch sizing, widening lists)
+    std::vector<int> h_lens, h_est, h_motif_len, h_read_locus;
+    std::vector<long long> h_read_begin;
+    int max_n1 = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// init / destroy
+// ------------------------------------------------------------------------------------------------
+static void build_lut(unsigned char lut[256]) {
+    // parasail matrix_create mapper: alphabet "ACGTRYSWKMBDHVNX" (align_matrix.py:25), case-insensitive,
+    // everything else -> the wildcard column (index 16)
+    const char *alpha = "ACGTRYSWKMBDHVNX";
+    for (int i = 0; i < 256; ++i) lut[i] = 16;
+    for (int i = 0; i < 16; ++i) {
+        lut[(unsigned char)alpha[i]] = (unsigned char)i;
+        lut[(unsigned char)(alpha[i] - 'A' + 'a')] = (unsigned char)i;
+    }
+}
+
+extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM], int gap_open, int gap_extend,
+                         int end_flags, int tie_flags, strk_ctx **out) {
+    if (!out || !matrix) return set_err(STRK_ERR_ARG, "strk_init: null argument");
+    *out = nullptr;
+    if (gap_open != gap_extend)
+        return set_err(STRK_ERR_UNSUPPORTED,
+                       "gap_open (%d) != gap_extend (%d): only the linear-gap case the reference uses "
+                       "(indel_penalty for both, repeats.py:33) is implemented",
+                       gap_open, gap_extend);
+    if (gap_open < 1 || gap_open > 60) return set_err(STRK_ERR_ARG, "gap penalty %d out of range [1, 60]", gap_open);
+    if (end_flags < 0 || end_flags > 15) return set_err(STRK_ERR_ARG, "end_flags %d out of range", end_flags);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_CUDA, "no CUDA device available (%s); strkit_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n_dev) return set_err(STRK_ERR_ARG, "device %d out of range (%d devices)", device, n_dev);
+    CU(cudaSetDevice(device));
+    strk_ctx *ctx = new (std::nothrow) strk_ctx();
+    if (!ctx) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->gap = gap_open;
+    ctx->end_flags = end_flags;
+    ctx->tie_flags = tie_flags;
+    build_lut(ctx->h_consts.lut);
+    for (int a = 0; a < STRK_NSYM; ++a)
+        for (int b = 0; b < STRK_NSYM; ++b) {
+            int v = matrix[a * STRK_NSYM + b];
+            if (v < -60 || v > 60) {
+                delete ctx;
+                return set_err(STRK_ERR_ARG, "matrix entry %d out of range [-60, 60]", v);
+            }
+            ctx->h_consts.smat[a * STRK_NSYM + b] = (signed char)v;
+        }
+    for (int b = 0; b < STRK_NSYM; ++b) {
+        ctx->h_consts.smat[STRK_PAD_FREE * STRK_NSYM + b] = 0;
+        ctx->h_consts.smat[STRK_PAD_PEN * STRK_NSYM + b] = (signed char)(-2 * gap_open);
+    }
+    ctx->h_consts.gap = gap_open;
+    ctx->h_consts.end_flags = end_flags;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void **)&ctx->d_consts, sizeof(ScoreConsts)));
+    CU(cudaMemcpy(ctx->d_consts, &ctx->h_consts, sizeof(ScoreConsts), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&ctx->d_queue, 4 * sizeof(unsigned int)));
+    CU(cudaMalloc((void **)&ctx->d_acc, 4 * sizeof(double)));
+    for (int k = 0; k < 3; ++k) CU(cudaEventCreate(&ctx->ev[k]));
+    *out = ctx;
+    return STRK_OK;
+}
+
+extern "C" int strk_destroy(strk_ctx *ctx) {
+    if (!ctx) return STRK_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->scratch.release();
+    ctx->fams.release();
+    ctx->table.release();
+    ctx->table64.release();
+    ctx->list_a.release();
+    ctx->list_b.release();
+    ctx->list_c.release();
+    if (ctx->d_consts) cudaFree(ctx->d_consts);
+    if (ctx->d_queue) cudaFree(ctx->d_queue);
+    if (ctx->d_acc) cudaFree(ctx->d_acc);
+    for (int k = 0; k < 3; ++k)
+        if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return STRK_OK;
+}
+
+extern "C" int strk_host_register(void *ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return set_err(STRK_ERR_ARG, "strk_host_register: null/empty buffer");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return STRK_OK;
+}
+extern "C" int strk_host_unregister(void *ptr) {
+    if (!ptr) return set_err(STRK_ERR_ARG, "strk_host_unregister: null buffer");
+    CU(cudaHostUnregister(ptr));
+    return STRK_OK;
+}
+
+extern "C" int strk_get_stats(strk_ctx *ctx, double stats[8]) {
+    if (!ctx || !stats) return set_err(STRK_ERR_ARG, "strk_get_stats: null argument");
+    memcpy(stats, ctx->stats, sizeof(ctx->stats));
+    return STRK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// validation shared by every entry point that takes sequences
+// ------------------------------------------------------------------------------------------------
+static int validate_reads(const char *who, uint64_t arena_bytes, const uint64_t *seq_off, const int32_t *lens,
+                          int64_t n_reads) {
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int a = lens[3 * r], b = lens[3 * r + 1], c = lens[3 * r + 2];
+        if (a < 0 || b < 0 || c < 0) return set_err(STRK_ERR_ARG, "%s: read %lld has a negative length", who, (long long)r);
+        const int64_t n1 = (int64_t)a + b + c;
+        if (n1 <= 0) return set_err(STRK_ERR_ARG, "%s: read %lld is empty (fl + tr + fr has no bases)", who, (long long)r);
+        if (n1 > (1 << 24)) return set_err(STRK_ERR_ARG, "%s: read %lld is too long (%lld)", who, (long long)r, (long long)n1);
+        if (seq_off[r] + (uint64_t)n1 > arena_bytes)
+            return set_err(STRK_ERR_ARG, "%s: read %lld runs past the end of the arena", who, (long long)r);
+    }
+    return STRK_OK;
+}
+
+static int validate_motifs(const char *who, uint64_t arena_bytes, const uint64_t *motif_off, const int32_t *motif_len,
+                           int64_t n) {
+    for (int64_t l = 0; l < n; ++l) {
+        if (motif_len[l] <= 0) return set_err(STRK_ERR_ARG, "%s: motif %lld is empty", who, (long long)l);
+        if (motif_off[l] + (uint64_t)motif_len[l] > arena_bytes)
+            return set_err(STRK_ERR_ARG, "%s: motif %lld runs past the end of the arena", who, (long long)l);
+    }
+    return STRK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// general DP launch
+// ------------------------------------------------------------------------------------------------
+static const int GEN_THREADS = 256;
+
+static int general_grid(strk_ctx *ctx, long long n_fams) {
+    long long warps_needed = n_fams;
+    long long blocks = (warps_needed + (GEN_THREADS / 32) - 1) / (GEN_THREADS / 32);
+    long long cap = (long long)ctx->n_sm * 4;  // persistent: up to 4 CTAs of 8 warps per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// scratch: per warp [b_len ints][rowlen ints][rowlen ints]
+static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const int *d_order, long long n_fams,
+                          const unsigned char *d_arena, void *d_table, int b_len, int rowlen, cudaStream_t st) {
+    if (n_fams <= 0) return STRK_OK;
+    if (n_fams > 0x7fffffffLL) return set_err(STRK_ERR_ARG, "too many families in one launch");
+    const int grid = general_grid(ctx, n_fams);
+    const size_t per_warp = (size_t)b_len + 2 * (size_t)rowlen;
+    const size_t total = per_warp * (size_t)grid * (GEN_THREADS / 32);
+    if (ctx->scratch.reserve(total) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of DP scratch", total * sizeof(int));
+    }
+    CU(cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), st));
+    if (ref)
+        dp_general_kernel<true><<<grid, GEN_THREADS, 0, st>>>(d_fams, d_order, (int)n_fams, d_arena, ctx->d_consts,
+                                                              d_table, ctx->scratch.p, rowlen, b_len, ctx->d_queue);
+    else
+        dp_general_kernel<false><<<grid, GEN_THREADS, 0, st>>>(d_fams, d_order, (int)n_fams, d_arena, ctx->d_consts,
+                                                               d_table, ctx->scratch.p, rowlen, b_len, ctx->d_queue);
+    CU(cudaGetLastError());
+    ctx->stats[2] += 1;
+    return STRK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batches
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st) {
+    cudaError_t e = cudaMalloc((void **)dst, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b) {
+    if (!b) return STRK_OK;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(b->d_arena);
+    cudaFree(b->d_seq_off);
+    cudaFree(b->d_motif_off);
+    cudaFree(b->d_lens);
+    cudaFree(b->d_est);
+    cudaFree(b->d_motif_len);
+    cudaFree(b->d_read_locus);
+    cudaFree(b->d_order);
+    cudaFree(b->d_read_begin);
+    cudaFree(b->d_out);
+    cudaFree(b->d_status);
+    delete b;
+    return STRK_OK;
+}
+
+extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                                 const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                                 const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci,
+                                 strk_batch **out) {
+    if (!ctx || !out) return set_err(STRK_ERR_ARG, "strk_batch_upload: null context/output");
+    *out = nullptr;
+    if (n_reads < 0 || n_loci < 0 || n_reads > 0x7ffffff0LL || n_loci > 0x7ffffff0LL)
+        return set_err(STRK_ERR_ARG, "strk_batch_upload: bad counts (%lld reads, %lld loci)", (long long)n_reads,
+                       (long long)n_loci);
+    if ((n_reads && (!arena || !seq_off || !lens || !est_cn)) || !read_begin || (n_loci && (!motif_off || !motif_len)))
+        return set_err(STRK_ERR_ARG, "strk_batch_upload: null array");
+    if (read_begin[0] != 0 || read_begin[n_loci] != n_reads)
+        return set_err(STRK_ERR_ARG, "strk_batch_upload: read_begin must run from 0 to n_reads");
+    for (int64_t l = 0; l < n_loci; ++l)
+        if (read_begin[l + 1] < read_begin[l]) return set_err(STRK_ERR_ARG, "strk_batch_upload: read_begin not monotone");
+    int rc = validate_reads("strk_batch_upload", arena_bytes, seq_off, lens, n_reads);
+    if (rc) return rc;
+    rc = validate_motifs("strk_batch_upload", arena_bytes, motif_off, motif_len, n_loci);
+    if (rc) return rc;
+    for (int64_t r = 0; r < n_reads; ++r)
+        if (est_cn[r] < 0 || est_cn[r] > (1 << 22))
+            return set_err(STRK_ERR_ARG, "strk_batch_upload: est_cn[%lld] = %d out of range", (long long)r, est_cn[r]);
+
+    CU(cudaSetDevice(ctx->device));
+    strk_batch *b = new (std::nothrow) strk_batch();
+    if (!b) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    b->n_reads = n_reads;
+    b->n_loci = n_loci;
+    b->h_lens.assign(lens, lens + 3 * n_reads);
+    b->h_est.assign(est_cn, est_cn + n_reads);
+    b->h_motif_len.assign(motif_len, motif_len + n_loci);
+    b->h_read_begin.assign(read_begin, read_begin + n_loci + 1);
+    b->h_read_locus.resize((size_t)n_reads);
+    for (int64_t l = 0; l < n_loci; ++l)
+        for (int64_t r = read_begin[l]; r < read_begin[l + 1]; ++r) b->h_read_locus[(size_t)r] = (int)l;
+
+    // cost-sorted work order: longest db first (counting sort on n1)
+    int max_n1 = 0;
+    for (int64_t r = 0; r < n_reads; ++r) max_n1 = std::max(max_n1, lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]);
+    b->max_n1 = max_n1;
+    std::vector<int> order((size_t)n_reads);
+    {
+        std::vector<long long> cnt((size_t)max_n1 + 2, 0);
+        for (int64_t r = 0; r < n_reads; ++r) cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++;
+        long long acc = 0;
+        for (size_t k = 0; k < cnt.size(); ++k) {
+            long long c = cnt[k];
+            cnt[k] = acc;
+            acc += c;
+        }
+        for (int64_t r = 0; r < n_reads; ++r)
+            order[(size_t)cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++] = (int)r;
+    }
+
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+#define UP(dst, src, n)                                     \
+    if (e == cudaSuccess) e = upload(&b->dst, src, (size_t)(n), st)
+    UP(d_arena, arena, arena_bytes);
+    UP(d_seq_off, (const unsigned long long *)seq_off, n_reads);
+    UP(d_lens, lens, 3 * n_reads);
+    UP(d_est, est_cn, n_reads);
+    UP(d_read_begin, (const long long *)read_begin, n_loci + 1);
+    UP(d_motif_off, (const unsigned long long *)motif_off, n_loci);
+    UP(d_motif_len, motif_len, n_loci);
+    UP(d_read_locus, b->h_read_locus.data(), n_reads);
+    UP(d_order, order.data(), n_reads);
+#undef UP
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_out, (size_t)(n_reads ? n_reads : 1) * 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_status, (size_t)(n_loci ? n_loci : 1));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `order` and the caller's buffers may go away
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        strk_batch_free(ctx, b);
+        return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "strk_batch_upload: %s",
+                       cudaGetErrorString(e));
+    }
+    *out = b;
+    return STRK_OK;
+}
+
+// longest boundary row any multi-pass family of the slot list needs (+1), and the longest db (+1)
+static void scratch_dims(const strk_batch *b, const int *read_ids, long long n_slots, int wd, int *b_len,
+                         int *rowlen) {
+    int mx_n1 = 0, mx_cols = 0;
+    for (long long s = 0; s < n_slots; ++s) {
+        const long long r = read_ids ? read_ids[s] : s;
+        const int fl = b->h_lens[3 * r], tr = b->h_lens[3 * r + 1], fr = b->h_lens[3 * r + 2];
+        const int n1 = fl + tr + fr;
+        mx_n1 = std::max(mx_n1, n1);
+        if (n1 > 32 * 16) {
+            const int m = b->h_motif_len[(size_t)b->h_read_locus[(size_t)r]];
+            mx_cols = std::max(mx_cols, std::max(fl, fr) + m * (b->h_est[(size_t)r] + wd));
+        }
+    }
+    *b_len = mx_n1 + 1;
+    *rowlen = mx_cols + 2;
+}
+
+extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int local_search_range, int step_size,
+                              int kernel, void *stream) {
+    if (!ctx || !b) return set_err(STRK_ERR_ARG, "strk_batch_run: null argument");
+    if (max_iters < 0 || local_search_range < 0 || step_size < 0 || local_search_range > 1000 || step_size > 1000)
+        return set_err(STRK_ERR_ARG, "strk_batch_run: bad search parameters");
+    (void)kernel;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
+    if (b->n_reads == 0) {
+        return STRK_OK;
+    }
+    CU(cudaMemsetAsync(ctx->d_acc, 0, 4 * sizeof(double), st));
+
+    int wd = local_search_range + step_size + 4;
+    if (wd < 8) wd = 8;
+    long long n_slots = b->n_reads;
+    long long n_list = b->n_loci;
+    const int *d_read_ids = nullptr, *d_locus_ids = nullptr;
+    const long long *d_slot_begin = nullptr;
+    std::vector<int> h_read_ids, h_locus_ids;
+    std::vector<long long> h_slot_begin;
+    std::vector<unsigned char> h_status;
+    float ms_dp = 0.f, ms_replay = 0.f;
+
+    for (int pass = 0;; ++pass) {
+        if (wd > (STRK_MAX_WINDOW - 1) / 2) wd = (STRK_MAX_WINDOW - 1) / 2;
+        const int W = 2 * wd + 1;
+        if (ctx->fams.reserve((size_t)n_slots) != cudaSuccess || ctx->table.reserve((size_t)n_slots * (size_t)W) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(STRK_ERR_NOMEM, "cannot allocate score tables for %lld reads x %d sizes", n_slots, W);
+        }
+        int b_len, rowlen;
+        scratch_dims(b, pass ? h_read_ids.data() : nullptr, n_slots, wd, &b_len, &rowlen);
+        const int threads = 256;
+        plan_reads_kernel<<<(unsigned)((n_slots + threads - 1) / threads), threads, 0, st>>>(
+            d_read_ids, n_slots, b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_off, b->d_motif_len, wd,
+            W, ctx->fams.p, ctx->d_acc + 1);
+        CU(cudaGetLastError());
+        ctx->stats[2] += 1;
+        CU(cudaEventRecord(ctx->ev[0], st));
+        int rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots, b->d_arena, ctx->table.p,
+                                b_len, rowlen, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev[1], st));
+        CU(cudaMemsetAsync(ctx->d_queue + 1, 0, sizeof(unsigned int), st));
+        replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
+            ctx->table.p, W, wd, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
+            b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
+            ctx->d_queue + 1, ctx->d_acc);
+        CU(cudaGetLastError());
+        ctx->stats[2] += 1;
+        CU(cudaEventRecord(ctx->ev[2], st));
+        unsigned int miss = 0;
+        CU(cudaMemcpyAsync(&miss, ctx->d_queue + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        float t0 = 0.f, t1 = 0.f;
+        CU(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
+        CU(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
+        ms_dp += t0;
+        ms_replay += t1;
+        ctx->stats[7] += (double)n_slots;
+        if (miss == 0) break;
+
+        // widening pass: redo the loci whose search left the window (status 1); status 2 is an error
+        ctx->stats[5] += 1;
+        if (wd >= (STRK_MAX_WINDOW - 1) / 2)
+            return set_err(STRK_ERR_SEARCH, "search left the widest supported window (%d sizes)", STRK_MAX_WINDOW);
+        h_status.resize((size_t)b->n_loci);
+        CU(cudaMemcpy(h_status.data(), b->d_status, (size_t)b->n_loci, cudaMemcpyDeviceToHost));
+        std::vector<int> loci;
+        if (pass == 0) {
+            for (long long l = 0; l < b->n_loci; ++l)
+                if (h_status[(size_t)l]) loci.push_back((int)l);
+        } else {
+            for (int l : h_locus_ids)
+                if (h_status[(size_t)l]) loci.push_back(l);
+        }
+        h_locus_ids.swap(loci);
+        h_read_ids.clear();
+        h_slot_begin.clear();
+        for (int l : h_locus_ids) {
+            if (h_status[(size_t)l] == 2)
+                return set_err(STRK_ERR_SEARCH, "locus %d: the search scored no size (max_iters = %d)", l, max_iters);
+            h_slot_begin.push_back((long long)h_read_ids.size());
+            for (long long r = b->h_read_begin[(size_t)l]; r < b->h_read_begin[(size_t)l + 1]; ++r)
+                h_read_ids.push_back((int)r);
+        }
+        n_slots = (long long)h_read_ids.size();
+        n_list = (long long)h_locus_ids.size();
+        if (ctx->list_a.reserve(h_read_ids.size()) != cudaSuccess || ctx->list_b.reserve(h_locus_ids.size()) != cudaSuccess ||
+            ctx->list_c.reserve(h_slot_begin.size()) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(STRK_ERR_NOMEM, "cannot allocate widening lists");
+        }
+        CU(cudaMemcpyAsync(ctx->list_a.p, h_read_ids.data(), h_read_ids.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->list_b.p, h_locus_ids.data(), h_locus_ids.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->list_c.p, h_slot_begin.data(), h_slot_begin.size() * sizeof(long long),
+                           cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        d_read_ids = ctx->list_a.p;
+        d_locus_ids = ctx->list_b.p;
+        d_slot_begin = ctx->list_c.p;
+        wd *= 8;
+    }
+    double acc[2] = {0, 0};
+    CU(cudaMemcpy(acc, ctx->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    ctx->stats[0] = acc[1];
+    ctx->stats[1] = acc[0];
+    ctx->stats[3] = ms_dp;
+    ctx->stats[4] = ms_replay;
+    return STRK_OK;
+}
+
+extern "C" int strk_batch_download(strk_ctx *ctx, strk_batch *b, int32_t *out) {
+    if (!ctx || !b || (!out && b->n_reads)) return set_err(STRK_ERR_ARG, "strk_batch_download: null argument");
+    CU(cudaSetDevice(ctx->device));
+    if (b->n_reads) CU(cudaMemcpy(out, b->d_out, (size_t)b->n_reads * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    return STRK_OK;
+}
+
+extern "C" int strk_count_reads(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                                const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                                const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, int max_iters,
+                                int local_search_range, int step_size, int kernel, int32_t *out) {
+    strk_batch *b = nullptr;
+    int rc = strk_batch_upload(ctx, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len,
+                               n_loci, &b);
+    if (rc) return rc;
+    rc = strk_batch_run(ctx, b, max_iters, local_search_range, step_size, kernel, nullptr);
+    if (!rc) rc = strk_batch_download(ctx, b, out);
+    strk_batch_free(ctx, b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw tables (parity checks of the DP itself) and the reference-boundary path
+// ------------------------------------------------------------------------------------------------
+struct TmpDev {
+    std::vector<void *> ptrs;
+    ~TmpDev() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t up(T **dst, const T *src, size_t n) {
+        cudaError_t e = cudaMalloc((void **)dst, (n ? n : 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(*dst);
+        if (n && src) e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+};
+
+static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                         const int32_t *lens, const int32_t *motif_idx, const int32_t *n_lo, const int32_t *n_hi,
+                         int64_t n_reads, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_motifs,
+                         const uint64_t *out_off, void *out_host) {
+    const char *who = ref ? "strk_ref_boundary_tables" : "strk_score_tables";
+    if (!ctx || !arena || !seq_off || !lens || !n_lo || !n_hi || !motif_off || !motif_len || !out_off || !out_host)
+        return set_err(STRK_ERR_ARG, "%s: null argument", who);
+    if (n_reads <= 0 || n_reads > 0x7ffffff0LL) return set_err(STRK_ERR_ARG, "%s: bad family count", who);
+    int rc = validate_reads(who, arena_bytes, seq_off, lens, n_reads);
+    if (rc) return rc;
+    rc = validate_motifs(who, arena_bytes, motif_off, motif_len, n_motifs);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<FamDesc> fams((size_t)n_reads);
+    uint64_t total = 0;
+    int b_len = 1, rowlen = 2;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int64_t mi = motif_idx ? motif_idx[r] : r;
+        if (mi < 0 || mi >= n_motifs) return set_err(STRK_ERR_ARG, "%s: motif index out of range", who);
+        if (n_lo[r] < 0 || n_hi[r] < n_lo[r] || n_hi[r] > (1 << 22))
+            return set_err(STRK_ERR_ARG, "%s: bad size window [%d, %d] for family %lld", who, n_lo[r], n_hi[r], (long long)r);
+        FamDesc &f = fams[(size_t)r];
+        f.db_off = seq_off[r];
+        f.motif_off = motif_off[mi];
+        f.out_off = out_off[r];
+        f.n_fl = lens[3 * r];
+        f.n_tr = lens[3 * r + 1];
+        f.n_fr = lens[3 * r + 2];
+        f.m = motif_len[mi];
+        f.n_lo = n_lo[r];
+        f.n_hi = n_hi[r];
+        // an empty candidate has no alignment (parasail rejects empty sequences)
+        if (ref && f.n_lo == 0 && (f.n_fl == 0 || f.n_fr == 0))
+            return set_err(STRK_ERR_ARG, "%s: family %lld scores an empty candidate (n = 0 with an empty flank)", who,
+                           (long long)r);
+        if (!ref && f.n_lo == 0 && f.n_fl + f.n_fr == 0)
+            return set_err(STRK_ERR_ARG, "%s: family %lld scores an empty candidate (n = 0 without flanks)", who,
+                           (long long)r);
+        const int n1 = f.n_fl + f.n_tr + f.n_fr;
+        const int64_t cols = (int64_t)std::max(f.n_fl, f.n_fr) + (int64_t)f.m * f.n_hi;
+        if (cols > (1 << 26)) return set_err(STRK_ERR_ARG, "%s: candidate too long", who);
+        b_len = std::max(b_len, n1 + 1);
+        if (n1 > 32 * 16) rowlen = std::max(rowlen, (int)cols + 2);
+        total = std::max<uint64_t>(total, out_off[r] + (uint64_t)(f.n_hi - f.n_lo + 1));
+    }
+    TmpDev tmp;
+    unsigned char *d_arena = nullptr;
+    FamDesc *d_fams = nullptr;
+    cudaError_t e = tmp.up(&d_arena, arena, (size_t)arena_bytes);
+    if (e == cudaSuccess) e = tmp.up(&d_fams, fams.data(), fams.size());
+    void *d_table = nullptr;
+    const size_t elem = ref ? 2 * sizeof(long long) : sizeof(int);
+    if (e == cudaSuccess) {
+        e = cudaMalloc(&d_table, (size_t)total * elem);
+        if (e == cudaSuccess) tmp.ptrs.push_back(d_table);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "%s: %s", who, cudaGetErrorString(e));
+    }
+    for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
+    rc = launch_general(ctx, ref, d_fams, nullptr, n_reads, d_arena, d_table, b_len, rowlen, ctx->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ref) {
+        CU(cudaMemcpy(out_host, d_table, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+        // unpack (score, end_query) pairs: the device layout per family is [fwd keys W][rev keys W]
+        std::vector<long long> keys((size_t)total * 2);
+        CU(cudaMemcpy(keys.data(), d_table, keys.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        int32_t *o = (int32_t *)out_host;
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const FamDesc &f = fams[(size_t)r];
+            const int W = f.n_hi - f.n_lo + 1;
+            const long long *k0 = keys.data() + 2 * f.out_off;
+            for (int k = 0; k < W; ++k) {
+                int fs, fe, rs, re;
+                ref_unpack(k0[k], fs, fe);
+                ref_unpack(k0[W + k], rs, re);
+                int32_t *dst = o + 4 * (f.out_off + (uint64_t)k);
+                dst[0] = fs, dst[1] = fe, dst[2] = rs, dst[3] = re;
+            }
+        }
+    }
+    return STRK_OK;
+}
+
+extern "C" int strk_score_tables(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                                 const int32_t *lens, const int32_t *motif_idx, const int32_t *n_lo, const int32_t *n_hi,
+                                 int64_t n_reads, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_motifs,
+                                 const uint64_t *out_off, int kernel, int32_t *scores) {
+    (void)kernel;
+    return tables_common(ctx, false, arena, arena_bytes, seq_off, lens, motif_idx, n_lo, n_hi, n_reads, motif_off,
+                         motif_len, n_motifs, out_off, scores);
+}
+
+extern "C" int strk_ref_boundary_tables(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes,
+                                        const uint64_t *seq_off, const int32_t *lens, const int32_t *n_lo,
+                                        const int32_t *n_hi, int64_t n_loci, const uint64_t *motif_off,
+                                        const int32_t *motif_len, const uint64_t *out_off, int32_t *out) {
+    return tables_common(ctx, true, arena, arena_bytes, seq_off, lens, nullptr, n_lo, n_hi, n_loci, motif_off, motif_len,
+                         n_loci, out_off, out);
+}
+
+extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                               const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
+                               const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off,
+                               const int32_t *motif_len, int vcf_anchor_size, int respect_coords, int32_t *out) {
+    (void)ctx, (void)arena, (void)arena_bytes, (void)seq_off, (void)lens, (void)start_count, (void)ref_size;
+    (void)rc_params, (void)n_loci, (void)motif_off, (void)motif_len, (void)vcf_anchor_size, (void)respect_coords;
+    (void)out;
+    return set_err(STRK_ERR_UNSUPPORTED, "strk_ref_counts: not implemented yet");
+}

@@ -1,0 +1,278 @@
+// replay.cuh -- exact replay of the reference's hill-climb over precomputed score tables.
+//
+// The DP kernels score a whole window of candidate sizes in parallel; the reference instead walks
+// sizes serially (strkit_rust_ext.get_repeat_count, called at repeats.py:58-68; the in-tree
+// statement of the same search is repeats.py:100-156) and its answer depends on the start size,
+// the visitation order, the iteration budget and the tie-breaks -- it is NOT an arg-max.  These
+// routines run that search verbatim with every "score this size" replaced by a table look-up, so
+// the parallel sweep returns bit-identical (n, score, n_explored).  A look-up outside the table
+// window is reported as a miss; the host widens the window and runs the locus again.
+//
+// Also replayed here: the per-locus read loop of call_locus.py:1079,1129-1161 (start guess with the
+// carried offset fraction; float64, round-half-even like CPython's round()).
+#pragma once
+#include "strk_common.cuh"
+
+#define STRK_MAX_WINDOW 4100  // widest table row the replay can track (bitmap of visited sizes)
+#define STRK_SEEN_WORDS ((STRK_MAX_WINDOW + 31) / 32)
+
+struct ClimbResult {
+    int best_n, best_score, n_explored;
+    int status;  // 0 ok, 1 window miss, 2 nothing scored
+    double sum_n;  // sum of the sizes scored (for reference-equivalent cell counts)
+};
+
+struct SeenSet {
+    unsigned int w[STRK_SEEN_WORDS];
+    int lo, hi;
+    __host__ __device__ void reset(int lo_, int hi_) {
+        lo = lo_;
+        hi = hi_;
+        int nw = (hi_ - lo_ + 32) / 32;
+        for (int k = 0; k < nw; ++k) w[k] = 0u;
+    }
+    __host__ __device__ bool inside(int n) const { return n >= lo && n <= hi; }
+    // sizes outside the window can never have been scored
+    __host__ __device__ bool has(int n) const {
+        if (!inside(n)) return false;
+        int k = n - lo;
+        return (w[k >> 5] >> (k & 31)) & 1u;
+    }
+    __host__ __device__ void add(int n) {
+        int k = n - lo;
+        w[k >> 5] |= 1u << (k & 31);
+    }
+};
+
+// Single-score search (read path).  table[n - n_lo] for n in [n_lo, n_hi].
+__host__ __device__ inline ClimbResult climb_single(const int *table, int n_lo, int n_hi, int start_count,
+                                                    int max_iters, int range, int step, int tie_flags,
+                                                    SeenSet &seen) {
+    ClimbResult res;
+    res.best_n = 0;
+    res.best_score = 0;
+    res.n_explored = 0;
+    res.status = 0;
+    res.sum_n = 0.0;
+    seen.reset(n_lo, n_hi);
+    int st_size[4], st_dir[4];
+    int top = 0;
+    st_size[top] = start_count - step, st_dir[top++] = -1;
+    st_size[top] = start_count + step, st_dir[top++] = 1;
+    st_size[top] = start_count, st_dir[top++] = 0;
+    bool have_best = false;
+    const bool wide = step > range;
+    while (top > 0 && res.n_explored < max_iters) {
+        --top;
+        const int size = st_size[top], dir = st_dir[top];
+        if (size < 0) continue;
+        int start_size = size - ((dir < 1 || wide) ? range : 0);
+        if (start_size < 0) start_size = 0;
+        const int end_size = size + ((dir > -1 || wide) ? range : 0);
+        bool have = false;
+        int mv_size = 0, mv_score = 0;
+        for (int i = start_size; i <= end_size; ++i) {
+            if (!seen.inside(i)) {
+                res.status = 1;
+                return res;
+            }
+            const int sc = table[i - n_lo];
+            if (!seen.has(i)) {
+                seen.add(i);
+                ++res.n_explored;
+                res.sum_n += (double)i;
+                // final pick = first-inserted maximum (repeats.py:154) unless STRK_TIE_FINAL_LAST
+                if (!have_best || sc > res.best_score || ((tie_flags & 2) && sc == res.best_score)) {
+                    have_best = true;
+                    res.best_n = i;
+                    res.best_score = sc;
+                }
+            }
+            if (!have || sc > mv_score || ((tie_flags & 1) && sc == mv_score)) {
+                have = true;
+                mv_size = i;
+                mv_score = sc;
+            }
+        }
+        // at most one of the two pushes can fire, so the stack never exceeds 3 entries
+        if (mv_size > size) {
+            const int new_rc = mv_size + step;
+            if (!seen.has(new_rc) && new_rc >= 0) st_size[top] = new_rc, st_dir[top++] = 1;
+        }
+        if (mv_size < size) {
+            const int new_rc = mv_size - step;
+            if (!seen.has(new_rc) && new_rc >= 0) st_size[top] = new_rc, st_dir[top++] = -1;
+        }
+    }
+    if (!have_best) res.status = 2;
+    return res;
+}
+
+struct RefClimbResult {
+    int l_offset, r_offset, n_offset_scores;
+    int status;
+};
+
+// Dual-score search of get_ref_repeat_count (repeats.py:100-169).  tab[k] for k = n - n_lo holds the
+// packed ARGMAX keys: fwd at tab[k], rev at tab[W + k]; score = key >> 32,
+// end_query = 0x7fffffff - (key & 0xffffffff) - 1.
+__host__ __device__ inline void ref_unpack(long long key, int &score, int &end_query) {
+    score = (int)(key >> 32);
+    end_query = 0x7fffffff - (int)(unsigned)(key & 0xffffffffll) - 1;
+}
+
+__host__ __device__ inline RefClimbResult climb_ref(const long long *tab, int n_lo, int n_hi, int start_count,
+                                                   int max_iters, int range, int step, int n_fl, int n_fr,
+                                                   int ref_size, int vcf_anchor_size, SeenSet &seen) {
+    RefClimbResult res;
+    res.l_offset = res.r_offset = res.n_offset_scores = 0;
+    res.status = 0;
+    const int W = n_hi - n_lo + 1;
+    seen.reset(n_lo, n_hi);
+    int st_size[4], st_dir[4];
+    int top = 0;
+    st_size[top] = start_count - step, st_dir[top++] = -1;
+    st_size[top] = start_count + step, st_dir[top++] = 1;
+    st_size[top] = start_count, st_dir[top++] = 0;
+    bool have_best = false;
+    int bf_score = 0, bf_adj = 0, br_score = 0, br_adj = 0;
+    const bool wide = step > range;
+    while (top > 0 && res.n_offset_scores < max_iters) {
+        --top;
+        const int size = st_size[top], dir = st_dir[top];
+        if (size < 0) continue;
+        int start_size = size - ((dir < 1 || wide) ? range : 0);
+        if (start_size < 0) start_size = 0;
+        const int end_size = size + ((dir > -1 || wide) ? range : 0);
+        bool have = false;
+        int mv_size = 0, mv_s = 0, mv_a = 0;
+        // max((*fwd_scores, *rev_scores), key=(score, adj)): first maximal, fwd entries first (:135)
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = start_size; i <= end_size; ++i) {
+                if (!seen.inside(i)) {
+                    res.status = 1;
+                    return res;
+                }
+                int fs, fe, rs, re;
+                ref_unpack(tab[i - n_lo], fs, fe);
+                ref_unpack(tab[W + i - n_lo], rs, re);
+                const int r_adj = fe + 1 - n_fl - ref_size;  // :34
+                const int l_adj = re + 1 - n_fr - ref_size;  // :41
+                if (!seen.has(i)) {
+                    seen.add(i);
+                    ++res.n_offset_scores;
+                    if (!have_best || fs > bf_score) bf_score = fs, bf_adj = r_adj;  // :154
+                    if (!have_best || rs > br_score) br_score = rs, br_adj = l_adj;  // :156
+                    have_best = true;
+                }
+                const int s = pass == 0 ? fs : rs, a = pass == 0 ? r_adj : l_adj;
+                if (!have || s > mv_s || (s == mv_s && a > mv_a)) {
+                    have = true;
+                    mv_size = i;
+                    mv_s = s;
+                    mv_a = a;
+                }
+            }
+        }
+        if (mv_size > size) {
+            const int new_rc = mv_size + step;
+            if (!seen.has(new_rc) && new_rc >= 0) st_size[top] = new_rc, st_dir[top++] = 1;
+        }
+        if (mv_size < size) {
+            const int new_rc = mv_size - step;
+            if (!seen.has(new_rc) && new_rc >= 0) st_size[top] = new_rc, st_dir[top++] = -1;
+        }
+    }
+    if (!have_best) {
+        res.status = 2;
+        return res;
+    }
+    res.l_offset = br_adj;  // :161
+    res.r_offset = bf_adj;  // :162
+    if (res.l_offset >= n_fl - vcf_anchor_size) res.l_offset = 0;  // :164-167
+    if (res.r_offset >= n_fr) res.r_offset = 0;                    // :168-169
+    return res;
+}
+
+// One thread per locus: the read loop of call_locus.py:1129-1161 over the score tables.
+//   table row of slot s = table + s * W ; window of the slot = [max(0, est - wd), est + wd]
+//   locus_ids == nullptr: locus q is q and its slots are read_begin[q]..; otherwise the widening
+//   pass lists the loci to redo and slot_begin[q] is the first slot of locus_ids[q].
+__global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd, const int *__restrict__ locus_ids,
+                                    const long long *__restrict__ slot_begin, int n_list,
+                                    const long long *__restrict__ read_begin, const int *__restrict__ est_cn,
+                                    const int *__restrict__ lens, const int *__restrict__ motif_len, int max_iters,
+                                    int range, int step, int tie_flags, int *__restrict__ out,
+                                    unsigned char *__restrict__ locus_status, unsigned int *miss_count,
+                                    double *ref_cells) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_list) return;
+    const int locus = locus_ids ? locus_ids[q] : q;
+    const long long r0 = read_begin[locus], r1 = read_begin[locus + 1];
+    long long slot = locus_ids ? slot_begin[q] : r0;
+    SeenSet seen;
+    double frac = 0.0;  // read_offset_frac_from_starting_guess (:1079)
+    double cells = 0.0;
+    const int m = motif_len[locus];
+    int status = 0;
+    for (long long r = r0; r < r1; ++r, ++slot) {
+        const int est = est_cn[r];
+        int read_sc = est;
+        const int off = (int)rint(frac * (double)read_sc);  // round(), :1130
+        if (off < -read_sc)
+            frac = 0.0;  // :1133
+        else
+            read_sc += off;  // :1136
+        const int n_lo = est - wd > 0 ? est - wd : 0;
+        const int n_hi = est + wd;
+        ClimbResult cr =
+            climb_single(table + (size_t)slot * (size_t)W, n_lo, n_hi, read_sc, max_iters, range, step, tie_flags, seen);
+        if (cr.status) {
+            status = cr.status;
+            break;
+        }
+        out[4 * r + 0] = cr.best_n;
+        out[4 * r + 1] = cr.best_score;
+        out[4 * r + 2] = cr.n_explored;
+        out[4 * r + 3] = read_sc;
+        frac += (double)(cr.best_n - read_sc) / (double)(cr.best_n > 1 ? cr.best_n : 1);  // :1161
+        const double n1 = (double)(lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]);
+        cells += n1 * ((double)cr.n_explored * (double)(lens[3 * r] + lens[3 * r + 2]) + (double)m * cr.sum_n);
+    }
+    locus_status[locus] = (unsigned char)status;
+    if (status)
+        atomicAdd(miss_count, 1u);
+    else
+        atomicAdd(ref_cells, cells);
+}
+
+// Builds the family descriptors of a pass on the device (no descriptor H2D traffic).
+//   read_ids == nullptr: slot s is read s.
+__global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_slots,
+                                  const unsigned long long *__restrict__ seq_off, const int *__restrict__ lens,
+                                  const int *__restrict__ est_cn, const int *__restrict__ read_locus,
+                                  const unsigned long long *__restrict__ motif_off, const int *__restrict__ motif_len,
+                                  int wd, int W, FamDesc *__restrict__ fams, double *exec_cells) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double cells = 0.0;
+    if (s < n_slots) {
+    const long long r = read_ids ? read_ids[s] : s;
+    const int locus = read_locus[r];
+    FamDesc f;
+    f.db_off = seq_off[r];
+    f.motif_off = motif_off[locus];
+    f.out_off = (unsigned long long)s * (unsigned long long)W;
+    f.n_fl = lens[3 * r];
+    f.n_tr = lens[3 * r + 1];
+    f.n_fr = lens[3 * r + 2];
+    f.m = motif_len[locus];
+    const int est = est_cn[r];
+    f.n_lo = est - wd > 0 ? est - wd : 0;
+    f.n_hi = est + wd;
+    fams[s] = f;
+    // executed DP cells: one forward sweep over fl + motif*n_hi plus one backward sweep over fr
+    cells = (double)(f.n_fl + f.n_tr + f.n_fr) * ((double)f.n_fl + (double)f.m * (double)f.n_hi + (double)f.n_fr);
+    }
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells > 0.0) atomicAdd(exec_cells, cells);
+}

@@ -1,0 +1,36 @@
+// strk_common.cuh -- shared device/host definitions for the B200 repeat-count kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define STRK_WARP 32
+#define STRK_NSYM_ 17
+#define STRK_PAD_FREE 17    // pad-row code when the top border is free   (score  0)
+#define STRK_PAD_PEN 18     // pad-row code when the top border is penalised (score -2g)
+#define STRK_SMAT_ROWS 19
+
+// One alignment family: a read (or a reference window) against every candidate fl + motif*n + fr.
+// db = fl + tr + fr is contiguous in the arena (reference strkit/call/repeats.py:91).
+struct FamDesc {
+    unsigned long long db_off;     // arena offset of fl + tr + fr
+    unsigned long long motif_off;  // arena offset of the motif
+    unsigned long long out_off;    // element offset of this family's row in the output table
+    int n_fl, n_tr, n_fr, m;
+    int n_lo, n_hi;                // candidate sizes [n_lo, n_hi]
+};
+
+// Scoring constants resident on the device (one copy per context).
+struct ScoreConsts {
+    unsigned char lut[256];                        // ASCII -> symbol code 0..16 (case-insensitive)
+    signed char smat[STRK_SMAT_ROWS * STRK_NSYM_]; // [row symbol or pad][column symbol]
+    int gap;
+    int end_flags;
+};
+
+__host__ __device__ inline int strk_pick_rows(int n1) {
+    // rows per lane of the strip layout: smallest R in the instantiated set with 32*R >= n1
+    const int set[12] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16};
+    for (int k = 0; k < 12; ++k)
+        if (32 * set[k] >= n1) return set[k];
+    return 16;
+}

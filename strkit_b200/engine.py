@@ -1,0 +1,171 @@
+"""Engine: one native context (one GPU) + the calls the batcher makes across the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _native
+from ._native import check, lib
+from .align_matrix import dna_matrix, indel_penalty
+from .batcher import ReadBatch
+from .repeat_count_params import RepeatCountParams
+
+__all__ = ["Engine", "DeviceBatch", "default_engine", "MODE_SG", "MODE_SG_QE", "KERNEL_AUTO", "KERNEL_GENERAL"]
+
+MODE_SG = 15      # parasail "sg": all four ends free (the mode the read path is believed to use)
+MODE_SG_QE = 2    # parasail "sg_qe" (repeats.py:33,40)
+KERNEL_AUTO = 0
+KERNEL_GENERAL = 1
+STAT_NAMES = ("executed_cells", "reference_cells", "kernel_launches", "dp_ms", "replay_ms", "widening_passes",
+              "reads_packed_kernel", "reads_general_kernel")
+
+
+def _p(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class DeviceBatch:
+    """A ReadBatch resident in HBM (strk_batch_upload)."""
+
+    def __init__(self, engine: "Engine", handle: int, n_reads: int, n_loci: int):
+        self.engine, self.handle, self.n_reads, self.n_loci = engine, handle, n_reads, n_loci
+
+    def free(self) -> None:
+        if self.handle:
+            lib.strk_batch_free(self.engine._ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device: int = 0, end_flags: int = MODE_SG, tie_flags: int = 0,
+                 matrix: np.ndarray = dna_matrix, gap_open: int = indel_penalty, gap_extend: int = indel_penalty):
+        mat = np.ascontiguousarray(matrix, dtype=np.int8)
+        if mat.shape != (17, 17):
+            raise ValueError("matrix must be 17x17")
+        ctx = C.c_void_p()
+        check(lib.strk_init(device, _p(mat), gap_open, gap_extend, end_flags, tie_flags, C.byref(ctx)))
+        self._ctx = ctx
+        self.device = device
+        self.end_flags = end_flags
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            lib.strk_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ read path
+    def upload(self, batch: ReadBatch) -> DeviceBatch:
+        batch.validate()
+        h = C.c_void_p()
+        check(lib.strk_batch_upload(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
+                                    _p(batch.est_cn), batch.n_reads, _p(batch.read_begin), _p(batch.motif_off),
+                                    _p(batch.motif_len), batch.n_loci, C.byref(h)))
+        return DeviceBatch(self, h, batch.n_reads, batch.n_loci)
+
+    def run(self, dbatch: DeviceBatch, rc_params: RepeatCountParams, kernel: int = KERNEL_AUTO, stream: int = 0) -> None:
+        check(lib.strk_batch_run(self._ctx, dbatch.handle, rc_params.max_iters, rc_params.initial_local_search_range,
+                                 rc_params.initial_step_size, kernel, C.c_void_p(stream)))
+
+    def download(self, dbatch: DeviceBatch, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((dbatch.n_reads, 4), dtype=np.int32)
+        check(lib.strk_batch_download(self._ctx, dbatch.handle, _p(out)))
+        return out
+
+    def count_reads(self, batch: ReadBatch, rc_params: RepeatCountParams, kernel: int = KERNEL_AUTO,
+                    out: np.ndarray | None = None) -> np.ndarray:
+        """out[r] = (best_n, best_score, n_explored, start_count used); host buffers in, host buffer out."""
+        batch.validate()
+        if out is None:
+            out = np.empty((batch.n_reads, 4), dtype=np.int32)
+        check(lib.strk_count_reads(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
+                                   _p(batch.est_cn), batch.n_reads, _p(batch.read_begin), _p(batch.motif_off),
+                                   _p(batch.motif_len), batch.n_loci, rc_params.max_iters,
+                                   rc_params.initial_local_search_range, rc_params.initial_step_size, kernel, _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ raw tables
+    def score_tables(self, batch: ReadBatch, n_lo: np.ndarray, n_hi: np.ndarray, kernel: int = KERNEL_AUTO):
+        """Scores of every candidate size in [n_lo[r], n_hi[r]] for every read; returns (scores, out_off)."""
+        batch.validate()
+        n_lo = np.ascontiguousarray(n_lo, dtype=np.int32)
+        n_hi = np.ascontiguousarray(n_hi, dtype=np.int32)
+        width = (n_hi.astype(np.int64) - n_lo + 1)
+        out_off = np.zeros(batch.n_reads, dtype=np.uint64)
+        out_off[1:] = np.cumsum(width)[:-1]
+        scores = np.empty(int(width.sum()), dtype=np.int32)
+        motif_idx = np.repeat(np.arange(batch.n_loci, dtype=np.int32), np.diff(batch.read_begin)).astype(np.int32)
+        check(lib.strk_score_tables(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
+                                    _p(motif_idx), _p(n_lo), _p(n_hi), batch.n_reads, _p(batch.motif_off),
+                                    _p(batch.motif_len), batch.n_loci, _p(out_off), kernel, _p(scores)))
+        return scores, out_off
+
+    def ref_boundary_tables(self, batch: ReadBatch, n_lo: np.ndarray, n_hi: np.ndarray):
+        """score_ref_boundaries for a window of sizes; one 'read' (the reference window) per locus.
+        Returns (table[k] = (fwd_score, fwd_end_query, rev_score, rev_end_query), out_off)."""
+        batch.validate()
+        if batch.n_reads != batch.n_loci:
+            raise ValueError("reference batches hold exactly one sequence per locus")
+        n_lo = np.ascontiguousarray(n_lo, dtype=np.int32)
+        n_hi = np.ascontiguousarray(n_hi, dtype=np.int32)
+        width = (n_hi.astype(np.int64) - n_lo + 1)
+        out_off = np.zeros(batch.n_loci, dtype=np.uint64)
+        out_off[1:] = np.cumsum(width)[:-1]
+        out = np.empty((int(width.sum()), 4), dtype=np.int32)
+        check(lib.strk_ref_boundary_tables(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off),
+                                           _p(batch.lens), _p(n_lo), _p(n_hi), batch.n_loci, _p(batch.motif_off),
+                                           _p(batch.motif_len), _p(out_off), _p(out)))
+        return out, out_off
+
+    def ref_counts(self, batch: ReadBatch, start_count, ref_size, rc_params, vcf_anchor_size: int,
+                   respect_coords: bool = False) -> np.ndarray:
+        """get_ref_repeat_count for every locus of a reference batch; rc_params int32 [n_loci, 3]."""
+        batch.validate()
+        start_count = np.ascontiguousarray(start_count, dtype=np.int32)
+        ref_size = np.ascontiguousarray(ref_size, dtype=np.int32)
+        rc = np.ascontiguousarray(rc_params, dtype=np.int32).reshape(batch.n_loci, 3)
+        out = np.empty((batch.n_loci, 8), dtype=np.int32)
+        check(lib.strk_ref_counts(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
+                                  _p(start_count), _p(ref_size), _p(rc), batch.n_loci, _p(batch.motif_off),
+                                  _p(batch.motif_len), vcf_anchor_size, int(respect_coords), _p(out)))
+        return out
+
+    def stats(self) -> dict[str, float]:
+        s = np.zeros(8, dtype=np.float64)
+        check(lib.strk_get_stats(self._ctx, _p(s)))
+        return dict(zip(STAT_NAMES, s.tolist()))
+
+
+_default: dict[tuple[int, int, int], Engine] = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device: int = 0, end_flags: int = MODE_SG, tie_flags: int = 0) -> Engine:
+    """Per-process engine used by the drop-in get_repeat_count / get_ref_repeat_count wrappers."""
+    key = (device, end_flags, tie_flags)
+    with _default_lock:
+        eng = _default.get(key)
+        if eng is None:
+            eng = _default[key] = Engine(device, end_flags, tie_flags)
+        return eng
+
+
+def device_count() -> int:
+    return int(lib.strk_device_count())
+
+
+_ = _native  # keep the loader import explicit: importing this module requires the native library

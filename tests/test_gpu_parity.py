@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+Run on the GPU box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+from tests.helpers import families_to_batch, oracle_tables, random_families
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import strkit_b200
+
+    assert strkit_b200.device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return strkit_b200
+
+
+@pytest.mark.parametrize("flags", list(range(16)))
+def test_score_tables_all_modes_small(sb, oracle, flags):
+    rng = np.random.default_rng(100 + flags)
+    fams = random_families(rng, 120)
+    n_lo, n_hi = [], []
+    for motif, tr, fl, fr in fams:
+        e = round(len(tr) / len(motif))
+        lo = max(0, e - int(rng.integers(0, 5)))
+        if lo == 0 and len(fl) + len(fr) == 0:
+            lo = 1  # an empty candidate has no alignment
+        n_lo.append(lo)
+        n_hi.append(lo + int(rng.integers(0, 9)))
+    eng = sb.Engine(end_flags=flags)
+    got, _ = eng.score_tables(families_to_batch(fams), np.array(n_lo), np.array(n_hi))
+    want = oracle_tables(oracle, fams, n_lo, n_hi, flags)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    eng.close()
+
+
+def test_score_tables_known_answers(sb):
+    """exact tract => score(k) = 2L, score(k+1) = 2L - 5m (any mode)."""
+    rng = np.random.default_rng(5)
+    eng = sb.Engine()
+    fams, ks = [], []
+    for _ in range(32):
+        m = int(rng.integers(2, 7))
+        while True:
+            motif = "".join(rng.choice(list("ACGT"), size=m))
+            if all(motif != motif[p:] + motif[:p] for p in range(1, m)):
+                break
+        k = int(rng.integers(8, 60))
+        while True:
+            fl = "".join(rng.choice(list("ACGT"), size=70))
+            fr = "".join(rng.choice(list("ACGT"), size=70))
+            if fl[-m:] != motif and fr[:m] != motif:
+                break
+        fams.append((motif, motif * k, fl, fr))
+        ks.append(k)
+    ks = np.array(ks)
+    got, off = eng.score_tables(families_to_batch(fams), ks, ks + 1)
+    for i, (motif, tr, fl, fr) in enumerate(fams):
+        L = 140 + len(tr)
+        assert got[int(off[i])] == 2 * L and got[int(off[i]) + 1] == 2 * L - 5 * len(motif)
+
+
+def test_get_repeat_count_golden(sb, golden):
+    """The drop-in per-call API against the committed vectors (reference dispatcher + restated search)."""
+    for c in golden["read_restated"]:
+        params = sb.RepeatCountParams("repalign", c["max_iters"], c["local_search_range"], c["step_size"])
+        (n, s), n_exp, delta = sb.get_repeat_count(c["start_count"], c["tr_seq"], c["flank_left_seq"],
+                                                   c["flank_right_seq"], c["motif"], params)
+        assert [n, s, n_exp, delta] == c["expect"], c
+
+
+def test_batch_config1_bit_exact(sb, oracle):
+    from strkit_b200 import synth
+
+    batch = synth.generate(synth.CONFIGS[1], 300, seed=11).to_host()
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    got = eng.count_reads(batch, params)
+    want, cells = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                    batch.motif_off, batch.motif_len, n_threads=8)
+    assert np.array_equal(got, want), np.flatnonzero((got != want).any(axis=1))[:10]
+    st = eng.stats()
+    assert st["reference_cells"] == cells  # the replay scored exactly the sizes the reference scores
+    assert 0 < st["executed_cells"] < cells
+
+
+def test_batch_noisy_ont_and_bad_estimates_force_widening(sb, oracle):
+    """Config-3-like reads with start estimates far off: the search leaves the first table window and
+    the widening passes must still reproduce the reference trajectory exactly."""
+    from strkit_b200 import synth
+
+    batch = synth.generate(synth.CONFIGS[3], 60, seed=12).to_host()
+    rng = np.random.default_rng(3)
+    est = batch.est_cn.copy()
+    bad = rng.random(est.shape[0]) < 0.2
+    est[bad] = np.maximum(0, est[bad] + rng.integers(-30, 60, int(bad.sum())))
+    batch.est_cn = est.astype(np.int32)
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    got = eng.count_reads(batch, params)
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                batch.motif_off, batch.motif_len, n_threads=8)
+    assert np.array_equal(got, want), np.flatnonzero((got != want).any(axis=1))[:10]
+    assert eng.stats()["widening_passes"] >= 1
+
+
+@pytest.mark.parametrize("params", [(7, 3, 1), (50, 3, 2), (50, 1, 4), (200, 3, 3), (0, 3, 1)])
+def test_batch_search_parameters(sb, oracle, params):
+    from strkit_b200 import synth
+    from strkit_b200._native import StrkError
+
+    batch = synth.generate(synth.CONFIGS[1], 40, seed=13).to_host()
+    p = sb.RepeatCountParams("repalign", *params)
+    eng = sb.Engine()
+    if params[0] == 0:  # nothing scored: the reference raises ValueError (max() of an empty dict)
+        with pytest.raises(StrkError):
+            eng.count_reads(batch, p)
+        return
+    got = eng.count_reads(batch, p)
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                batch.motif_off, batch.motif_len, max_iters=params[0], local_search_range=params[1],
+                                step_size=params[2], n_threads=8)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("tie", [1, 2, 3])
+def test_tie_break_switches(sb, oracle, tie):
+    rng = np.random.default_rng(9)
+    # homopolymer-ish tracts with wildcards produce many equal scores
+    fams = [("A", "A" * int(rng.integers(3, 20)) + "X" * int(rng.integers(0, 4)), "", "ACGTT") for _ in range(40)]
+    batch = families_to_batch(fams, est=[int(rng.integers(0, 25)) for _ in fams])
+    eng = sb.Engine(tie_flags=tie)
+    got = eng.count_reads(batch, sb.RepeatCountParams("repalign", 50, 3, 1))
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                batch.motif_off, batch.motif_len, tie_flags=tie)
+    assert np.array_equal(got, want)
+
+
+def test_long_expansions_multi_pass(sb, oracle):
+    """Config-4-like: tracts longer than one 512-row strip, IUPAC motifs, int32 range."""
+    from strkit_b200 import synth
+
+    batch, _ = synth.generate_expansions(n_loci=6, reads_per_locus=4, max_tract=1800, big_lo=150, big_hi=400)
+    eng = sb.Engine()
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    got = eng.count_reads(batch, params)
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                batch.motif_off, batch.motif_len, n_threads=8)
+    assert np.array_equal(got, want), (got[:8], want[:8])
+
+
+def test_ref_boundary_tables_golden(sb, oracle, golden):
+    eng = sb.Engine()
+    fams = [(c["motif"], c["tr_seq"], c["flank_left_seq"], c["flank_right_seq"]) for c in golden["boundaries"]]
+    ns = np.array([c["n"] for c in golden["boundaries"]])
+    lo = np.maximum(ns - 2, np.array([0 if (f[2] and f[3]) else 1 for f in fams]))
+    hi = ns + 2
+    tab, off = eng.ref_boundary_tables(families_to_batch(fams), lo, hi)
+    for i, c in enumerate(golden["boundaries"]):
+        fs, fe, rs, re = (int(v) for v in tab[int(off[i]) + c["n"] - int(lo[i])])
+        r_adj = fe + 1 - len(c["flank_left_seq"]) - c["ref_size"]
+        l_adj = re + 1 - len(c["flank_right_seq"]) - c["ref_size"]
+        assert [fs, r_adj, rs, l_adj] == c["expect"], c
+        for n in range(int(lo[i]), int(hi[i]) + 1):  # the rest of the window against the oracle
+            (ofs, ora), (ors, ola) = oracle.score_ref_boundaries(c["tr_seq"], c["flank_left_seq"],
+                                                                 c["flank_right_seq"], c["motif"], n, c["ref_size"])
+            fs, fe, rs, re = (int(v) for v in tab[int(off[i]) + n - int(lo[i])])
+            assert (fs, fe + 1 - len(c["flank_left_seq"]) - c["ref_size"]) == (ofs, ora)
+            assert (rs, re + 1 - len(c["flank_right_seq"]) - c["ref_size"]) == (ors, ola)
+
+
+def test_invalid_inputs_raise(sb):
+    from strkit_b200._native import StrkError
+
+    eng = sb.Engine()
+    p = sb.RepeatCountParams("repalign", 50, 3, 1)
+    with pytest.raises(StrkError):
+        eng.count_reads(families_to_batch([("CAG", "", "", "")], est=[0]), p)  # empty db
+    b = families_to_batch([("CAG", "CAGCAG", "AC", "GT")])
+    b.motif_len[0] = 0
+    with pytest.raises(StrkError):
+        eng.count_reads(b, p)
+    with pytest.raises(StrkError):
+        sb.Engine(gap_open=7, gap_extend=1)  # affine gaps are not what the reference uses
+    with pytest.raises(NotImplementedError):
+        sb.get_repeat_count(3, "CAGCAG", "A", "T", "CAG", sb.RepeatCountParams("comp", 50, 3, 1))

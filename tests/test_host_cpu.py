@@ -1,0 +1,95 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports what include/strkit_b200.h declares,
+fails loudly without a device, and the host batcher / generators behave."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from strkit_b200 import _native
+
+    header = open(os.path.join(ROOT, "include", "strkit_b200.h")).read()
+    declared = set(re.findall(r"\b(strk_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 15
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.EXPORTED)
+    assert _native.lib.strk_version().decode().startswith("strkit_b200")
+
+
+def test_no_cpu_fallback_without_device():
+    import strkit_b200
+    from strkit_b200._native import StrkError
+
+    if strkit_b200.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(StrkError, match="no CPU fallback"):
+        strkit_b200.Engine()
+    with pytest.raises(StrkError):
+        strkit_b200.get_repeat_count(5, "CAGCAGCAGCAGCAG", "ACGT", "TTGA", "CAG",
+                                     strkit_b200.RepeatCountParams("repalign", 50, 3, 1))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "strkit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_matrix_matches_reference_golden(golden):
+    from strkit_b200.align_matrix import dna_bases_str, dna_matrix
+
+    assert dna_bases_str == golden["alphabet"]
+    assert dna_matrix.tolist() == golden["matrix"]
+
+
+def test_reference_rc_param_tiers():
+    from strkit_b200 import get_reference_rc_params as g
+
+    assert (g("repalign", 10, 250).max_iters, g("repalign", 10, 250).initial_step_size) == (250, 1)
+    p = g("repalign", 200, 250)
+    assert (p.max_iters, p.initial_step_size, p.initial_local_search_range) == (200, 3, 3)
+    p = g("repalign", 1999, 250)
+    assert (p.max_iters, p.initial_step_size, p.initial_local_search_range) == (150, 5, 3)
+    p = g("repalign", 2000, 250)
+    assert (p.max_iters, p.initial_step_size, p.initial_local_search_range) == (50, 15, 1)
+
+
+def test_pack_loci_layout():
+    from strkit_b200 import LocusReads, pack_loci
+
+    b = pack_loci([LocusReads("CAG", [2, 3], ["CAGCAG", "CAGCAGCAG"], ["AA", "AC"], ["TT", "T"]),
+                   LocusReads("AT", [1], ["AT"], [""], ["GG"])])
+    b.validate()
+    assert b.n_reads == 3 and b.n_loci == 2
+    assert b.read_begin.tolist() == [0, 2, 3]
+    assert b.lens.tolist() == [[2, 6, 2], [2, 9, 1], [0, 2, 2]]
+    arena = bytes(b.arena)
+    assert arena[int(b.seq_off[1]):int(b.seq_off[1]) + 12] == b"ACCAGCAGCAGT"
+    assert arena[int(b.motif_off[1]):int(b.motif_off[1]) + 2] == b"AT"
+    s = b.slice_loci(1, 2)
+    assert s.n_reads == 1 and s.read_begin.tolist() == [0, 1] and s.lens.tolist() == [[0, 2, 2]]
+
+
+def test_synth_generator_is_deterministic_and_sane(oracle):
+    from strkit_b200 import synth
+
+    a = synth.generate(synth.CONFIGS[1], 50, seed=1).to_host()
+    b = synth.generate(synth.CONFIGS[1], 50, seed=1).to_host()
+    assert np.array_equal(a.arena, b.arena) and np.array_equal(a.lens, b.lens)
+    assert a.n_reads == 1500 and (a.lens[:, 0] <= 70).all() and (a.lens[:, 2] <= 70).all()
+    assert set(np.unique(a.arena)) <= set(b"ACGTX")
+    # the generator's copies are recovered by the reference search on almost every HiFi read
+    sb = synth.generate(synth.CONFIGS[1], 50, seed=1)
+    out, _ = oracle.count_loci(a.arena, a.seq_off, a.lens, a.est_cn, a.read_begin, a.motif_off, a.motif_len,
+                               n_threads=4)
+    assert (out[:, 0] == sb.true_cn.numpy()).mean() > 0.97
