@@ -397,7 +397,7 @@ static void scratch_dims(const strk_batch *b, const int *read_ids, long long n_s
             mx_cols = std::max(mx_cols, std::max(fl, fr) + m * (b->h_est[(size_t)r] + wd));
         }
     }
-    *b_len = mx_n1 + 1;
+    *b_len = mx_n1 + 2;
     *rowlen = mx_cols + 2;
 }
 
@@ -569,7 +569,7 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
     CU(cudaSetDevice(ctx->device));
     std::vector<FamDesc> fams((size_t)n_reads);
     uint64_t total = 0;
-    int b_len = 1, rowlen = 2;
+    int b_len = 2, rowlen = 2;
     for (int64_t r = 0; r < n_reads; ++r) {
         const int64_t mi = motif_idx ? motif_idx[r] : r;
         if (mi < 0 || mi >= n_motifs) return set_err(STRK_ERR_ARG, "%s: motif index out of range", who);
@@ -595,7 +595,7 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
         const int n1 = f.n_fl + f.n_tr + f.n_fr;
         const int64_t cols = (int64_t)std::max(f.n_fl, f.n_fr) + (int64_t)f.m * f.n_hi;
         if (cols > (1 << 26)) return set_err(STRK_ERR_ARG, "%s: candidate too long", who);
-        b_len = std::max(b_len, n1 + 1);
+        b_len = std::max(b_len, n1 + 2);
         if (n1 > 32 * 16) rowlen = std::max(rowlen, (int)cols + 2);
         total = std::max<uint64_t>(total, out_off[r] + (uint64_t)(f.n_hi - f.n_lo + 1));
     }

@@ -41,7 +41,8 @@ struct PassCfg {
     int s2_beg_free;      // top border is 0
     int kind;
     int lastrow_term;     // COMBINE with a free s2 end: candidates may stop early on the last row
-    int *B;               // [n1 + 1] DUMP writes, COMBINE reads
+    int *B;               // [n1 + 2] DUMP writes, COMBINE reads; B[n1 + 1] = best score of a path that
+                          // starts inside the suffix columns (free s2 begin), see dp_pass
     int *out;             // COMBINE: [n_hi - n_lo + 1], pre-set to STRK_NEG_INF
     long long *out64;     // ARGMAX: packed (score << 32 | 0x7fffffff - row), pre-set to LLONG_MIN
     int *row0, *row1;     // boundary-row scratch, ncols + 1 ints each (multi-pass families only)
@@ -71,6 +72,7 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
 
     if (c.kind == PASS_DUMP && c.ncols == 0) {  // no columns: the last column is the border
         for (int i = lane; i <= c.n1; i += 32) c.B[i] = border_col0(c, i, g);
+        if (lane == 0) c.B[c.n1 + 1] = border_col0(c, c.n1, g);
         __syncwarp();
         return;
     }
@@ -83,6 +85,7 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
             if (i == c.n1 && c.lastrow_term) b = -g;
             best = max(best, border_col0(c, i, g) + b);
         }
+        if (c.s2_beg_free && lane == 0) best = max(best, c.B[c.n1 + 1]);
         atomicMax(&c.out[0], best);
     }
 
@@ -170,6 +173,8 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
                     }
                     if (off == 0 && b == 0 && lane == 0) best = max(best, border_row0(c, j, g) + c.B[c.n1]);
                     if (c.lastrow_term && b == NB - 1 && lane == 31) best = max(best, pmax);
+                    // free s2 begin: a path may start on the top border to the right of this column
+                    if (c.s2_beg_free && b == NB - 1 && lane == 31) best = max(best, c.B[c.n1 + 1]);
                     atomicMax(&c.out[n - c.n_lo], best);
                 } else {  // ARGMAX over real rows i >= 1, smallest row on ties (parasail end_query = i - 1)
                     long long best = (long long)0x8000000000000000ull;
@@ -185,6 +190,9 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
                 }
             }
         }
+        // backward sweep: best value anywhere on its last row (= forward row 0, i.e. paths that skip the
+        // whole prefix through a free s2 begin), including the border cell
+        if (c.kind == PASS_DUMP && b == NB - 1 && lane == 31) c.B[c.n1 + 1] = max(pmax, border_col0(c, c.n1, g));
         __syncwarp();  // boundary row written by lane 31 is read by lane 0 in the next pass
     }
     (void)W;
