@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-read repeat-count hot path on synthetic HiFi reads.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path, host cores)
+
+A "step" is one pass of the hot path over one batch (loci_per_step loci x 30 reads, BASELINE config 2
+distributions: "synthetic genome-wide catalog 1M loci x 30x HiFi reads, loci sharded across GPUs").  The
+default K x loci_per_step is the full 1M-locus catalog on one GPU.  Multi-GPU: loci are sharded by catalog
+partition, one rank per GPU, NO collective on the data path (weak scaling: every rank gets its own
+loci_per_step per step); torch.distributed is used for the barriers and the max-over-ranks timing only.
+
+Printed JSON (one line, rank 0): metric / value = reads x loci per second with the batch resident in HBM;
+e2e = the same through the host-buffer C-ABI call (pinned host arenas, H2D + kernels + D2H inside the
+timed region); roofline = the DP kernel against the measured integer issue rate; cpu_baseline = the CPU
+oracle (a port of the reference's algorithm; the real parasail/strkit_rust_ext are not installable here)
+timed on this box's host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "read x locus repeat counts per second"
+UNIT = "reads*loci/s"
+READS_PER_LOCUS = 30
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--loci-per-step", type=int, default=32768)
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through (> L2)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "general"])
+    ap.add_argument("--cpu-sample-loci", type=int, default=768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"cfg2: synthetic genome-wide catalog, HiFi-like reads, motif 2-6 bp x 10-60 copies, "
+            f"{READS_PER_LOCUS} reads/locus, {args.loci_per_step} loci per step per GPU "
+            f"({args.steps * args.loci_per_step} loci per GPU in the timed region)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(batch, n_loci_sample, steps=1):
+    """The oracle (port of the reference's CPU algorithm) on the first n_loci_sample loci, all host cores."""
+    from tests import oracle_lib
+
+    orc = oracle_lib.load()
+    cores = os.cpu_count() or 1
+    sub = batch.slice_loci(0, min(n_loci_sample, batch.n_loci))
+    best, cells = None, 0.0
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        out, cells = orc.count_loci(sub.arena, sub.seq_off, sub.lens, sub.est_cn, sub.read_begin, sub.motif_off,
+                                    sub.motif_len, n_threads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": sub.n_reads / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {sub.n_loci} loci ({sub.n_reads} reads) of batch 0, {best:.2f} s, "
+                      f"{cells / best / 1e9:.2f} GCUPS reference-equivalent",
+            "gcups": cells / best / 1e9}, out, sub
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; parasail and
+    strkit_rust_ext cannot be installed here) on the host cores, same config / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch  # noqa: F401  (data synthesis only)
+
+    from strkit_b200 import synth
+
+    n_sample = args.cpu_sample_loci
+    t_all = time.perf_counter()
+    batch = synth.generate(synth.CONFIGS[2], n_sample, seed=20261018 + 2000, device="cpu").to_host()
+    from tests import oracle_lib
+
+    orc = oracle_lib.load()
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 4))
+    warm = min(args.warmup, 1)
+    times, cells = [], 0.0
+    for it in range(warm + steps):
+        t0 = time.perf_counter()
+        _, cells = orc.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                  batch.motif_off, batch.motif_len, n_threads=cores)
+        if it >= warm:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    value = batch.n_reads / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": f"{n_sample} loci x {READS_PER_LOCUS} reads per step"},
+            "gcups_reference_equivalent": cells / dt / 1e9,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} loci ({batch.n_reads} reads) per step, {steps} steps"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+
+    import strkit_b200
+    from strkit_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    eng = strkit_b200.Engine(device=local_rank)
+    params = strkit_b200.RepeatCountParams("repalign", 50, 3, 1)  # read-path defaults (params.py:45,157-163)
+    kernel = strkit_b200.KERNEL_GENERAL if args.kernel == "general" else strkit_b200.KERNEL_AUTO
+
+    # ---- synthetic catalog partition of this rank: `pool` distinct batches, generated on the GPU
+    host_batches, dev_batches = [], []
+    for p in range(args.pool):
+        sbatch = synth.generate(synth.CONFIGS[2], args.loci_per_step, seed=20261018 + 2000 + 100 * rank + p,
+                                device=str(dev), chunk_loci=4096)
+        hb = sbatch.to_host(pin=True)
+        del sbatch
+        host_batches.append(hb)
+        dev_batches.append(eng.upload(hb))
+    torch.cuda.empty_cache()
+    reads_per_step = host_batches[0].n_reads
+    pool_bytes = sum(b.nbytes() for b in host_batches)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- integer issue-rate peak (roofline denominator), measured on this GPU now
+    peak = eng.measure_int_peak()
+
+    # ---- warm-up
+    for w in range(args.warmup):
+        eng.run(dev_batches[w % args.pool], params, kernel, stream)
+
+    # ---- timed region: K steps, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {k: 0.0 for k in ("executed_cells", "reference_cells", "kernel_launches", "dp_ms", "replay_ms",
+                            "widening_passes", "reads_packed_kernel", "reads_general_kernel")}
+    ev0.record()
+    for k in range(args.steps):
+        eng.run(dev_batches[k % args.pool], params, kernel, stream)
+        st = eng.stats()
+        for key in agg:
+            agg[key] += st[key]
+    ev1.record()
+    barrier()
+    elapsed_ms = reduce_max(ev0.elapsed_time(ev1))
+    clocks = sampler.stop()
+    total_reads = reduce_sum(float(reads_per_step) * args.steps)
+    value = total_reads / (elapsed_ms * 1e-3)
+    exec_cells = reduce_sum(agg["executed_cells"])
+    ref_cells = reduce_sum(agg["reference_cells"])
+
+    # ---- e2e: host buffers through the C-ABI call (H2D + kernels + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 8)
+        outs = [np.empty((b.n_reads, 4), dtype=np.int32) for b in host_batches]
+        for o in outs:
+            strkit_b200._native.check(strkit_b200._native.lib.strk_host_register(o.ctypes.data, o.nbytes))
+        eng.count_reads(host_batches[0], params, kernel, out=outs[0])  # warm the recycled device buffers
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            eng.count_reads(host_batches[k % args.pool], params, kernel, out=outs[k % args.pool])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = reduce_max(dt)
+        e2e = {"value": reduce_sum(float(reads_per_step) * e2e_steps) / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(host_batches[0].nbytes() + 8 * reads_per_step),  # + plan arrays (order, locus)
+               "d2h_bytes_per_step": int(outs[0].nbytes), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
+
+    # ---- parity spot-check + CPU baseline on a bounded sample (rank 0)
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu, want, sub = cpu_baseline(host_batches[0], args.cpu_sample_loci)
+        got = eng.download(dev_batches[0])[:sub.n_reads] if args.warmup + args.steps > 0 else None
+        if args.pool and (args.steps + args.warmup) > 0:
+            # batch 0 was last run in the timed loop or warm-up; its device results are still resident
+            parity = bool(np.array_equal(got, want))
+
+    if rank == 0:
+        dp_s = agg["dp_ms"] * 1e-3
+        # dominant kernel = the DP kernel; algorithmic work = 4 int32 ops per executed cell
+        achieved = agg["executed_cells"] * 4.0 / dp_s / 1e12 if dp_s > 0 else 0.0
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        arena_gbs = (host_batches[0].nbytes() * args.steps) / dp_s / 1e9 if dp_s > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32" if args.kernel == "general" else "u16x2/int32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "reads_per_locus": READS_PER_LOCUS,
+                       "loci_per_step_per_gpu": args.loci_per_step, "search": "max_iters 50, range 3, step 1",
+                       "alignment": "parasail sg (all ends free), match 2 / mismatch -7 / indel 5",
+                       "l2": f"inputs larger than L2: pool of {args.pool} distinct batches, "
+                             f"{pool_bytes / 1e6:.0f} MB per GPU, cycled",
+                       "parallelism": f"catalog partition x{world}, no collective"},
+            "gcups_executed": exec_cells / (elapsed_ms * 1e-3) / 1e9,
+            "gcups_reference_equivalent": ref_cells / (elapsed_ms * 1e-3) / 1e9,
+            "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak["dual_pipe"], "unit": "Tiop/s",
+                         "frac": achieved / peak["dual_pipe"] if peak["dual_pipe"] else None, "traffic": None,
+                         "kernel": "dp_general_kernel" if agg["reads_packed_kernel"] == 0 else "dp_packed_kernel",
+                         "ops_per_cell": 4, "kernel_ms_per_step": agg["dp_ms"] / max(1, args.steps),
+                         "kernel_share_of_step": agg["dp_ms"] / elapsed_ms if elapsed_ms else None,
+                         "peak_how": "measured now on this GPU: lane-level 32-bit integer instructions/s, "
+                                     "VIADDMNMX + IMAD chains on both issue pipes (ALU-pipe only: "
+                                     f"{peak['alu_pipe']:.2f}, FMA-pipe only: {peak['fma_pipe']:.2f})",
+                         "hbm": {"achieved": arena_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "note": "arena streaming only; the path is INT-ALU bound, not HBM bound"}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(agg["kernel_launches"]),
+            "replay_ms_per_step": agg["replay_ms"] / max(1, args.steps),
+            "widening_passes": int(agg["widening_passes"]),
+            "reads_packed_kernel": int(agg["reads_packed_kernel"]),
+            "reads_general_kernel": int(agg["reads_general_kernel"]),
+            "parity_sample_bit_exact": parity, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

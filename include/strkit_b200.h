@@ -147,6 +147,11 @@ int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, c
  *   stats[6] reads handled by the packed kernel   stats[7] reads handled by the general kernel */
 int strk_get_stats(strk_ctx *ctx, double stats[8]);
 
+/* Integer issue-rate micro-benchmark: the roofline denominator of the DP kernels (MEASURED_PEAKS.json has
+ * no INT32 figure).  out_tiops[0] = ALU pipe only (VIADDMNMX), [1] = FMA pipe only (IMAD), [2] = both pipes;
+ * units: 1e12 lane-level 32-bit integer instructions per second, all SMs. */
+int strk_measure_int_peak(strk_ctx *ctx, double out_tiops[3]);
+
 #ifdef __cplusplus
 }
 #endif

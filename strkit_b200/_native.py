@@ -49,6 +49,7 @@ def _load() -> C.CDLL:
         "strk_ref_boundary_tables": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
         "strk_ref_counts": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
         "strk_get_stats": (C.c_int, [_vp, _vp]),
+        "strk_measure_int_peak": (C.c_int, [_vp, _vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib_, name)  # AttributeError here = header and library out of sync
@@ -60,7 +61,7 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTED = ("strk_last_error", "strk_version", "strk_device_count", "strk_init", "strk_destroy", "strk_host_register",
             "strk_host_unregister", "strk_batch_upload", "strk_batch_run", "strk_batch_download", "strk_batch_free",
-            "strk_count_reads", "strk_score_tables", "strk_ref_boundary_tables", "strk_ref_counts", "strk_get_stats")
+            "strk_count_reads", "strk_score_tables", "strk_ref_boundary_tables", "strk_ref_counts", "strk_get_stats", "strk_measure_int_peak")
 
 
 def check(rc: int) -> None:

@@ -8,6 +8,7 @@
 
 #include "../../include/strkit_b200.h"
 #include "dp_general.cuh"
+#include "int_peak.cuh"
 #include "replay.cuh"
 #include "strk_common.cuh"
 
@@ -85,10 +86,15 @@ struct strk_ctx {
     double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    struct strk_batch *reuse = nullptr;  // device buffers recycled by strk_count_reads
 };
 
 struct strk_batch {
     long long n_reads = 0, n_loci = 0;
+    DevBuf<unsigned char> arena, status;
+    DevBuf<unsigned long long> seq_off, motif_off;
+    DevBuf<int> lens, est, motif_len, read_locus, order, out;
+    DevBuf<long long> read_begin;
     unsigned char *d_arena = nullptr;
     unsigned long long *d_seq_off = nullptr, *d_motif_off = nullptr;
     int *d_lens = nullptr, *d_est = nullptr, *d_motif_len = nullptr, *d_read_locus = nullptr, *d_order = nullptr;
@@ -96,9 +102,13 @@ struct strk_batch {
     int *d_out = nullptr;
     unsigned char *d_status = nullptr;
     // host mirrors used for planning (scratch sizing, widening lists)
-    std::vector<int> h_lens, h_est, h_motif_len, h_read_locus;
+    std::vector<int> h_lens, h_est, h_motif_len, h_read_locus, h_order;
     std::vector<long long> h_read_begin;
     int max_n1 = 0;
+    void release() {
+        arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
+        motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -170,10 +180,14 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     return STRK_OK;
 }
 
+extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b);
+
 extern "C" int strk_destroy(strk_ctx *ctx) {
     if (!ctx) return STRK_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->reuse) strk_batch_free(ctx, ctx->reuse);
+    ctx->reuse = nullptr;
     ctx->scratch.release();
     ctx->fams.release();
     ctx->table.release();
@@ -277,57 +291,43 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
 // batches
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st) {
-    cudaError_t e = cudaMalloc((void **)dst, (n ? n : 1) * sizeof(T));
+static cudaError_t upload(DevBuf<T> &buf, T **dst, const T *src, size_t n, cudaStream_t st) {
+    cudaError_t e = buf.reserve(n ? n : 1);
     if (e != cudaSuccess) return e;
-    if (n) e = cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    *dst = buf.p;
+    if (n) e = cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
     return e;
 }
 
 extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b) {
     if (!b) return STRK_OK;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(b->d_arena);
-    cudaFree(b->d_seq_off);
-    cudaFree(b->d_motif_off);
-    cudaFree(b->d_lens);
-    cudaFree(b->d_est);
-    cudaFree(b->d_motif_len);
-    cudaFree(b->d_read_locus);
-    cudaFree(b->d_order);
-    cudaFree(b->d_read_begin);
-    cudaFree(b->d_out);
-    cudaFree(b->d_status);
+    b->release();
     delete b;
     return STRK_OK;
 }
 
-extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
-                                 const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
-                                 const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci,
-                                 strk_batch **out) {
-    if (!ctx || !out) return set_err(STRK_ERR_ARG, "strk_batch_upload: null context/output");
-    *out = nullptr;
+// validate + plan + H2D into (possibly recycled) device buffers
+static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                      const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci) {
     if (n_reads < 0 || n_loci < 0 || n_reads > 0x7ffffff0LL || n_loci > 0x7ffffff0LL)
-        return set_err(STRK_ERR_ARG, "strk_batch_upload: bad counts (%lld reads, %lld loci)", (long long)n_reads,
-                       (long long)n_loci);
+        return set_err(STRK_ERR_ARG, "batch: bad counts (%lld reads, %lld loci)", (long long)n_reads, (long long)n_loci);
     if ((n_reads && (!arena || !seq_off || !lens || !est_cn)) || !read_begin || (n_loci && (!motif_off || !motif_len)))
-        return set_err(STRK_ERR_ARG, "strk_batch_upload: null array");
+        return set_err(STRK_ERR_ARG, "batch: null array");
     if (read_begin[0] != 0 || read_begin[n_loci] != n_reads)
-        return set_err(STRK_ERR_ARG, "strk_batch_upload: read_begin must run from 0 to n_reads");
+        return set_err(STRK_ERR_ARG, "batch: read_begin must run from 0 to n_reads");
     for (int64_t l = 0; l < n_loci; ++l)
-        if (read_begin[l + 1] < read_begin[l]) return set_err(STRK_ERR_ARG, "strk_batch_upload: read_begin not monotone");
-    int rc = validate_reads("strk_batch_upload", arena_bytes, seq_off, lens, n_reads);
+        if (read_begin[l + 1] < read_begin[l]) return set_err(STRK_ERR_ARG, "batch: read_begin not monotone");
+    int rc = validate_reads("batch", arena_bytes, seq_off, lens, n_reads);
     if (rc) return rc;
-    rc = validate_motifs("strk_batch_upload", arena_bytes, motif_off, motif_len, n_loci);
+    rc = validate_motifs("batch", arena_bytes, motif_off, motif_len, n_loci);
     if (rc) return rc;
     for (int64_t r = 0; r < n_reads; ++r)
         if (est_cn[r] < 0 || est_cn[r] > (1 << 22))
-            return set_err(STRK_ERR_ARG, "strk_batch_upload: est_cn[%lld] = %d out of range", (long long)r, est_cn[r]);
+            return set_err(STRK_ERR_ARG, "batch: est_cn[%lld] = %d out of range", (long long)r, est_cn[r]);
 
     CU(cudaSetDevice(ctx->device));
-    strk_batch *b = new (std::nothrow) strk_batch();
-    if (!b) return set_err(STRK_ERR_NOMEM, "out of host memory");
     b->n_reads = n_reads;
     b->n_loci = n_loci;
     b->h_lens.assign(lens, lens + 3 * n_reads);
@@ -342,7 +342,8 @@ extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t a
     int max_n1 = 0;
     for (int64_t r = 0; r < n_reads; ++r) max_n1 = std::max(max_n1, lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]);
     b->max_n1 = max_n1;
-    std::vector<int> order((size_t)n_reads);
+    std::vector<int> &order = b->h_order;
+    order.resize((size_t)n_reads);
     {
         std::vector<long long> cnt((size_t)max_n1 + 2, 0);
         for (int64_t r = 0; r < n_reads; ++r) cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++;
@@ -358,26 +359,44 @@ extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t a
 
     cudaStream_t st = ctx->stream;
     cudaError_t e = cudaSuccess;
-#define UP(dst, src, n)                                     \
-    if (e == cudaSuccess) e = upload(&b->dst, src, (size_t)(n), st)
-    UP(d_arena, arena, arena_bytes);
-    UP(d_seq_off, (const unsigned long long *)seq_off, n_reads);
-    UP(d_lens, lens, 3 * n_reads);
-    UP(d_est, est_cn, n_reads);
-    UP(d_read_begin, (const long long *)read_begin, n_loci + 1);
-    UP(d_motif_off, (const unsigned long long *)motif_off, n_loci);
-    UP(d_motif_len, motif_len, n_loci);
-    UP(d_read_locus, b->h_read_locus.data(), n_reads);
-    UP(d_order, order.data(), n_reads);
+#define UP(buf, dst, src, n) \
+    if (e == cudaSuccess) e = upload(b->buf, &b->dst, src, (size_t)(n), st)
+    UP(arena, d_arena, (const unsigned char *)arena, arena_bytes);
+    UP(seq_off, d_seq_off, (const unsigned long long *)seq_off, n_reads);
+    UP(lens, d_lens, (const int *)lens, 3 * n_reads);
+    UP(est, d_est, (const int *)est_cn, n_reads);
+    UP(read_begin, d_read_begin, (const long long *)read_begin, n_loci + 1);
+    UP(motif_off, d_motif_off, (const unsigned long long *)motif_off, n_loci);
+    UP(motif_len, d_motif_len, (const int *)motif_len, n_loci);
+    UP(read_locus, d_read_locus, (const int *)b->h_read_locus.data(), n_reads);
+    UP(order, d_order, (const int *)order.data(), n_reads);
 #undef UP
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_out, (size_t)(n_reads ? n_reads : 1) * 4 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_status, (size_t)(n_loci ? n_loci : 1));
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `order` and the caller's buffers may go away
+    if (e == cudaSuccess) e = b->out.reserve((size_t)(n_reads ? n_reads : 1) * 4);
+    if (e == cudaSuccess) e = b->status.reserve((size_t)(n_loci ? n_loci : 1));
+    b->d_out = b->out.p;
+    b->d_status = b->status.p;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the caller's buffers may go away after return
     if (e != cudaSuccess) {
         cudaGetLastError();
-        strk_batch_free(ctx, b);
-        return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "strk_batch_upload: %s",
+        return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "batch upload: %s",
                        cudaGetErrorString(e));
+    }
+    return STRK_OK;
+}
+
+extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                                 const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                                 const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci,
+                                 strk_batch **out) {
+    if (!ctx || !out) return set_err(STRK_ERR_ARG, "strk_batch_upload: null context/output");
+    *out = nullptr;
+    strk_batch *b = new (std::nothrow) strk_batch();
+    if (!b) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    int rc = batch_fill(ctx, b, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len,
+                        n_loci);
+    if (rc) {
+        strk_batch_free(ctx, b);
+        return rc;
     }
     *out = b;
     return STRK_OK;
@@ -526,13 +545,15 @@ extern "C" int strk_count_reads(strk_ctx *ctx, const uint8_t *arena, uint64_t ar
                                 const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
                                 const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, int max_iters,
                                 int local_search_range, int step_size, int kernel, int32_t *out) {
-    strk_batch *b = nullptr;
-    int rc = strk_batch_upload(ctx, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len,
-                               n_loci, &b);
+    if (!ctx) return set_err(STRK_ERR_ARG, "strk_count_reads: null context");
+    if (!ctx->reuse) ctx->reuse = new (std::nothrow) strk_batch();
+    if (!ctx->reuse) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    strk_batch *b = ctx->reuse;  // device buffers are recycled across calls (no cudaMalloc per block of loci)
+    int rc = batch_fill(ctx, b, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len,
+                        n_loci);
     if (rc) return rc;
     rc = strk_batch_run(ctx, b, max_iters, local_search_range, step_size, kernel, nullptr);
     if (!rc) rc = strk_batch_download(ctx, b, out);
-    strk_batch_free(ctx, b);
     return rc;
 }
 
@@ -666,4 +687,39 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
     (void)rc_params, (void)n_loci, (void)motif_off, (void)motif_len, (void)vcf_anchor_size, (void)respect_coords;
     (void)out;
     return set_err(STRK_ERR_UNSUPPORTED, "strk_ref_counts: not implemented yet");
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer issue-rate micro-benchmark (roofline denominator)
+// ------------------------------------------------------------------------------------------------
+extern "C" int strk_measure_int_peak(strk_ctx *ctx, double out_tiops[3]) {
+    if (!ctx || !out_tiops) return set_err(STRK_ERR_ARG, "strk_measure_int_peak: null argument");
+    CU(cudaSetDevice(ctx->device));
+    int *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_out, sizeof(int)));
+    const int grid = ctx->n_sm * 8, threads = 256, iters = 4096;
+    const double instr = (double)grid * threads * (double)iters * 64.0;  // lane-level integer instructions
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int mode = 0; mode < 3; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(e0, ctx->stream));
+            if (mode == 0) int_peak_kernel<0><<<grid, threads, 0, ctx->stream>>>(iters, rep + 3, d_out);
+            if (mode == 1) int_peak_kernel<1><<<grid, threads, 0, ctx->stream>>>(iters, rep + 3, d_out);
+            if (mode == 2) int_peak_kernel<2><<<grid, threads, 0, ctx->stream>>>(iters, rep + 3, d_out);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        out_tiops[mode] = instr / ((double)best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return STRK_OK;
 }

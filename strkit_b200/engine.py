@@ -144,6 +144,12 @@ class Engine:
                                   _p(batch.motif_len), vcf_anchor_size, int(respect_coords), _p(out)))
         return out
 
+    def measure_int_peak(self) -> dict[str, float]:
+        """Measured integer issue rates (1e12 lane-instructions/s): the DP kernels' roofline denominator."""
+        s = np.zeros(3, dtype=np.float64)
+        check(lib.strk_measure_int_peak(self._ctx, _p(s)))
+        return {"alu_pipe": float(s[0]), "fma_pipe": float(s[1]), "dual_pipe": float(s[2])}
+
     def stats(self) -> dict[str, float]:
         s = np.zeros(8, dtype=np.float64)
         check(lib.strk_get_stats(self._ctx, _p(s)))
