@@ -8,6 +8,7 @@
 
 #include "../../include/strkit_b200.h"
 #include "dp_general.cuh"
+#include "dp_packed.cuh"
 #include "int_peak.cuh"
 #include "replay.cuh"
 #include "strk_common.cuh"
@@ -82,6 +83,7 @@ struct strk_ctx {
     DevBuf<long long> table64;
     DevBuf<int> list_a, list_b;      // widening-pass lists
     DevBuf<long long> list_c;
+    DevBuf<int> fallback;            // reads the packed kernel handed to the general kernel
     unsigned int *d_queue = nullptr;  // [0] work queue, [1] miss counter
     double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -105,6 +107,10 @@ struct strk_batch {
     std::vector<int> h_lens, h_est, h_motif_len, h_read_locus, h_order;
     std::vector<long long> h_read_begin;
     int max_n1 = 0;
+    // work plan over h_order: [0, n_general) general-kernel-only reads, then one segment per packed R
+    long long n_general = 0;
+    long long bin_off[9] = {0}, bin_cnt[9] = {0};  // index R / 2
+    int bin_mmax[9] = {0}, bin_flank[9] = {0};
     void release() {
         arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
         motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
@@ -170,6 +176,34 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     }
     ctx->h_consts.gap = gap_open;
     ctx->h_consts.end_flags = end_flags;
+    {
+        // PRMT tables of the packed kernel: byte c of t8[b] = score(row class c, column symbol b) + 2g
+        static const int class_code[7] = {0, 1, 2, 3, 14, 15, 16};  // A C G T N X other
+        int ok = 1;
+        for (int b = 0; b < STRK_NSYM; ++b) {
+            unsigned long long tf = 0, tb = 0;
+            for (int c = 0; c < 7; ++c) {
+                int v = matrix[class_code[c] * STRK_NSYM + b] + 2 * gap_open;
+                if (v < 0 || v > 127) ok = 0;
+                tf |= (unsigned long long)(v & 0xff) << (8 * c);
+            }
+            tb = tf;
+            tf |= (unsigned long long)((end_flags & STRK_S2_BEG_FREE) ? 2 * gap_open : 0) << 56;
+            tb |= (unsigned long long)((end_flags & STRK_S2_END_FREE) ? 2 * gap_open : 0) << 56;
+            ctx->h_consts.t8f[b] = tf;
+            ctx->h_consts.t8b[b] = tb;
+        }
+        for (int a = 0; a < STRK_NSYM; ++a)
+            for (int b = 0; b < STRK_NSYM; ++b) {
+                int v = matrix[a * STRK_NSYM + b] + 2 * gap_open;
+                if (v < 0 || v > 127) ok = 0;
+            }
+        for (int k = 0; k <= STRK_SMAT_ROWS; ++k) ctx->h_consts.cls_of[k] = 0x80;
+        for (int c = 0; c < 7; ++c) ctx->h_consts.cls_of[class_code[c]] = (unsigned char)c;
+        ctx->h_consts.cls_of[STRK_PAD_FREE] = 7;
+        ctx->h_consts.cls_of[STRK_PAD_PEN] = 7;
+        ctx->h_consts.packed_ok = ok;
+    }
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&ctx->d_consts, sizeof(ScoreConsts)));
     CU(cudaMemcpy(ctx->d_consts, &ctx->h_consts, sizeof(ScoreConsts), cudaMemcpyHostToDevice));
@@ -195,6 +229,7 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     ctx->list_a.release();
     ctx->list_b.release();
     ctx->list_c.release();
+    ctx->fallback.release();
     if (ctx->d_consts) cudaFree(ctx->d_consts);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     if (ctx->d_acc) cudaFree(ctx->d_acc);
@@ -265,8 +300,11 @@ static int general_grid(strk_ctx *ctx, long long n_fams) {
 
 // scratch: per warp [b_len ints][rowlen ints][rowlen ints]
 static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const int *d_order, long long n_fams,
-                          const unsigned char *d_arena, void *d_table, int b_len, int rowlen, cudaStream_t st) {
+                          const unsigned char *d_arena, void *d_table, int b_len, int rowlen, cudaStream_t st,
+                          const unsigned int *d_count = nullptr) {
+    // d_count != nullptr: the list length lives on the device; n_fams is only its upper bound
     if (n_fams <= 0) return STRK_OK;
+    if (d_count && n_fams > (long long)ctx->n_sm * (GEN_THREADS / 32)) n_fams = (long long)ctx->n_sm * (GEN_THREADS / 32);
     if (n_fams > 0x7fffffffLL) return set_err(STRK_ERR_ARG, "too many families in one launch");
     const int grid = general_grid(ctx, n_fams);
     const size_t per_warp = (size_t)b_len + 2 * (size_t)rowlen;
@@ -278,13 +316,57 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
     CU(cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), st));
     if (ref)
         dp_general_kernel<true><<<grid, GEN_THREADS, 0, st>>>(d_fams, d_order, (int)n_fams, d_arena, ctx->d_consts,
-                                                              d_table, ctx->scratch.p, rowlen, b_len, ctx->d_queue);
+                                                              d_table, ctx->scratch.p, rowlen, b_len, ctx->d_queue,
+                                                              d_count);
     else
         dp_general_kernel<false><<<grid, GEN_THREADS, 0, st>>>(d_fams, d_order, (int)n_fams, d_arena, ctx->d_consts,
-                                                               d_table, ctx->scratch.p, rowlen, b_len, ctx->d_queue);
+                                                               d_table, ctx->scratch.p, rowlen, b_len, ctx->d_queue,
+                                                               d_count);
     CU(cudaGetLastError());
     ctx->stats[2] += 1;
     return STRK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed DP launch (one template instantiation per R)
+// ------------------------------------------------------------------------------------------------
+static const int PK_WARPS = 4;
+
+static size_t packed_smem_bytes(int R, const PackedSmemDims &d) {
+    const int fcol_words = d.w_max * (R / 2) * 32, bq_words = (R / 2) * 32;
+    const int per_warp16 = d.colt_entries + (d.prof_words + fcol_words + bq_words + 2 * d.w_max + 3) / 4 + 1;
+    return (size_t)per_warp16 * 16 * PK_WARPS;
+}
+
+template <int R>
+static cudaError_t launch_packed_r(const FamDesc *fams, const int *list, int n, const unsigned char *arena,
+                                   const ScoreConsts *consts, int *table, PackedSmemDims dims, int *fb_list,
+                                   unsigned int *fb_count, cudaStream_t st) {
+    const size_t smem = packed_smem_bytes(R, dims);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dp_packed_kernel<R><<<(n + PK_WARPS - 1) / PK_WARPS, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, consts, table, dims,
+                                                                                     fb_list, fb_count);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_packed(int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
+                                 const ScoreConsts *consts, int *table, PackedSmemDims dims, int *fb_list,
+                                 unsigned int *fb_count, cudaStream_t st) {
+    switch (R) {
+        case 2: return launch_packed_r<2>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 4: return launch_packed_r<4>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 6: return launch_packed_r<6>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 8: return launch_packed_r<8>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 10: return launch_packed_r<10>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 12: return launch_packed_r<12>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 14: return launch_packed_r<14>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        default: return launch_packed_r<16>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,12 +420,11 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     for (int64_t l = 0; l < n_loci; ++l)
         for (int64_t r = read_begin[l]; r < read_begin[l + 1]; ++r) b->h_read_locus[(size_t)r] = (int)l;
 
-    // cost-sorted work order: longest db first (counting sort on n1)
+    // cost-sorted work order: longest db first (counting sort on n1) ...
     int max_n1 = 0;
     for (int64_t r = 0; r < n_reads; ++r) max_n1 = std::max(max_n1, lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]);
     b->max_n1 = max_n1;
-    std::vector<int> &order = b->h_order;
-    order.resize((size_t)n_reads);
+    std::vector<int> sorted((size_t)n_reads);
     {
         std::vector<long long> cnt((size_t)max_n1 + 2, 0);
         for (int64_t r = 0; r < n_reads; ++r) cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++;
@@ -354,7 +435,44 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
             acc += c;
         }
         for (int64_t r = 0; r < n_reads; ++r)
-            order[(size_t)cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++] = (int)r;
+            sorted[(size_t)cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++] = (int)r;
+    }
+    // ... then segmented: reads only the general kernel can take, followed by one segment per packed R
+    std::vector<int> &order = b->h_order;
+    order.clear();
+    order.reserve((size_t)n_reads);
+    {
+        std::vector<unsigned char> bin((size_t)n_reads);
+        long long cnt[9] = {0};
+        for (int k = 0; k < 9; ++k) b->bin_mmax[k] = b->bin_flank[k] = 0;
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const int fl = lens[3 * r], fr = lens[3 * r + 2], n1 = fl + lens[3 * r + 1] + fr;
+            const int m = motif_len[(size_t)b->h_read_locus[(size_t)r]];
+            int R = ctx->h_consts.packed_ok ? strk_pick_rows_packed(n1) : 0;
+            if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128) R = 0;
+            bin[(size_t)r] = (unsigned char)(R / 2);
+            cnt[R / 2]++;
+            if (R) {
+                b->bin_mmax[R / 2] = std::max(b->bin_mmax[R / 2], m);
+                b->bin_flank[R / 2] = std::max(b->bin_flank[R / 2], std::max(fl, fr));
+            }
+        }
+        long long acc = 0;
+        b->n_general = cnt[0];
+        long long start[9];
+        start[0] = 0;
+        acc = cnt[0];
+        for (int k = 8; k >= 1; --k) {
+            start[k] = acc;
+            b->bin_off[k] = acc;
+            b->bin_cnt[k] = cnt[k];
+            acc += cnt[k];
+        }
+        order.resize((size_t)n_reads);
+        for (int64_t q = 0; q < n_reads; ++q) {
+            const int r = sorted[(size_t)q];
+            order[(size_t)start[bin[(size_t)r]]++] = r;
+        }
     }
 
     cudaStream_t st = ctx->stream;
@@ -425,7 +543,6 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
     if (!ctx || !b) return set_err(STRK_ERR_ARG, "strk_batch_run: null argument");
     if (max_iters < 0 || local_search_range < 0 || step_size < 0 || local_search_range > 1000 || step_size > 1000)
         return set_err(STRK_ERR_ARG, "strk_batch_run: bad search parameters");
-    (void)kernel;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
@@ -461,9 +578,49 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[0], st));
-        int rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots, b->d_arena, ctx->table.p,
+        int rc = STRK_OK;
+        const bool use_packed = pass == 0 && kernel != STRK_KERNEL_GENERAL && ctx->h_consts.packed_ok;
+        long long n_packed = 0;
+        if (!use_packed) {
+            rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots, b->d_arena, ctx->table.p,
                                 b_len, rowlen, st);
-        if (rc) return rc;
+            if (rc) return rc;
+        } else {
+            // pass 0: slot == read.  Packed kernel per R segment; what it cannot take goes to the general kernel.
+            if (ctx->fallback.reserve((size_t)b->n_reads) != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(STRK_ERR_NOMEM, "cannot allocate the fallback list");
+            }
+            CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
+            for (int k = 8; k >= 1; --k) {
+                if (!b->bin_cnt[k]) continue;
+                const int R = 2 * k;
+                PackedSmemDims dims;
+                dims.colt_entries = b->bin_flank[k] + 32;
+                dims.prof_words = b->bin_mmax[k] * R * 32;
+                dims.w_max = W;
+                cudaError_t e = cudaSuccess;
+                if (packed_smem_bytes(R, dims) > 200 * 1024) {
+                    // shared memory would not fit: hand the whole segment to the general kernel
+                    rc = launch_general(ctx, false, ctx->fams.p, b->d_order + b->bin_off[k], b->bin_cnt[k], b->d_arena,
+                                        ctx->table.p, b_len, rowlen, st);
+                    if (rc) return rc;
+                    continue;
+                }
+                e = launch_packed(R, ctx->fams.p, b->d_order + b->bin_off[k], (int)b->bin_cnt[k], b->d_arena, ctx->d_consts,
+                                  ctx->table.p, dims, ctx->fallback.p, ctx->d_queue + 2, st);
+                if (e != cudaSuccess) return set_err(STRK_ERR_CUDA, "packed kernel launch (R=%d): %s", R, cudaGetErrorString(e));
+                ctx->stats[2] += 1;
+                n_packed += b->bin_cnt[k];
+            }
+            rc = launch_general(ctx, false, ctx->fams.p, b->d_order, b->n_general, b->d_arena, ctx->table.p, b_len, rowlen, st);
+            if (rc) return rc;
+            if (n_packed) {
+                rc = launch_general(ctx, false, ctx->fams.p, ctx->fallback.p, n_packed, b->d_arena, ctx->table.p, b_len,
+                                    rowlen, st, ctx->d_queue + 2);
+                if (rc) return rc;
+            }
+        }
         CU(cudaEventRecord(ctx->ev[1], st));
         CU(cudaMemsetAsync(ctx->d_queue + 1, 0, sizeof(unsigned int), st));
         replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
@@ -473,9 +630,14 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[2], st));
-        unsigned int miss = 0;
-        CU(cudaMemcpyAsync(&miss, ctx->d_queue + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        unsigned int miss_fb[2] = {0, 0};  // [0] loci whose search left the window, [1] packed-kernel fallbacks
+        CU(cudaMemcpyAsync(miss_fb, ctx->d_queue + 1, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        const unsigned int miss = miss_fb[0];
+        if (use_packed) {
+            ctx->stats[6] += (double)(n_packed - (long long)miss_fb[1]);
+            ctx->stats[7] -= (double)(n_packed - (long long)miss_fb[1]);
+        }
         float t0 = 0.f, t1 = 0.f;
         CU(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
         CU(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
@@ -578,7 +740,7 @@ struct TmpDev {
 static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                          const int32_t *lens, const int32_t *motif_idx, const int32_t *n_lo, const int32_t *n_hi,
                          int64_t n_reads, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_motifs,
-                         const uint64_t *out_off, void *out_host) {
+                         const uint64_t *out_off, int kernel, void *out_host) {
     const char *who = ref ? "strk_ref_boundary_tables" : "strk_score_tables";
     if (!ctx || !arena || !seq_off || !lens || !n_lo || !n_hi || !motif_off || !motif_len || !out_off || !out_host)
         return set_err(STRK_ERR_ARG, "%s: null argument", who);
@@ -636,8 +798,68 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
         return set_err(STRK_ERR_NOMEM, "%s: %s", who, cudaGetErrorString(e));
     }
     for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
-    rc = launch_general(ctx, ref, d_fams, nullptr, n_reads, d_arena, d_table, b_len, rowlen, ctx->stream);
-    if (rc) return rc;
+    if (ref || kernel == STRK_KERNEL_GENERAL || !ctx->h_consts.packed_ok) {
+        rc = launch_general(ctx, ref, d_fams, nullptr, n_reads, d_arena, d_table, b_len, rowlen, ctx->stream);
+        if (rc) return rc;
+    } else {
+        // same routing as strk_batch_run: packed kernel per R, the rest (and its fallbacks) to the general kernel
+        std::vector<int> lists[9];
+        int mmax[9] = {0}, flank[9] = {0}, wmax[9] = {0};
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const FamDesc &f = fams[(size_t)r];
+            int R = strk_pick_rows_packed(f.n_fl + f.n_tr + f.n_fr);
+            if (f.n_fl < 1 || f.n_fr < 1 || f.n_fl > PK_FLANK_MAX || f.n_fr > PK_FLANK_MAX || f.m * R > 128 ||
+                f.n_hi - f.n_lo + 1 > 64)
+                R = 0;
+            lists[R / 2].push_back((int)r);
+            mmax[R / 2] = std::max(mmax[R / 2], f.m);
+            flank[R / 2] = std::max(flank[R / 2], std::max(f.n_fl, f.n_fr));
+            wmax[R / 2] = std::max(wmax[R / 2], f.n_hi - f.n_lo + 1);
+        }
+        std::vector<int> flat;
+        size_t offs[9];
+        for (int k = 0; k < 9; ++k) {
+            offs[k] = flat.size();
+            flat.insert(flat.end(), lists[k].begin(), lists[k].end());
+        }
+        int *d_lists = nullptr, *d_fb = nullptr;
+        e = tmp.up(&d_lists, flat.data(), flat.size());
+        if (e == cudaSuccess) e = tmp.up(&d_fb, (const int *)nullptr, (size_t)n_reads);
+        if (e != cudaSuccess) return set_err(STRK_ERR_NOMEM, "%s: %s", who, cudaGetErrorString(e));
+        CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), ctx->stream));
+        long long n_packed = 0;
+        for (int k = 8; k >= 1; --k) {
+            if (lists[k].empty()) continue;
+            PackedSmemDims dims;
+            dims.colt_entries = flank[k] + 32;
+            dims.prof_words = mmax[k] * 2 * k * 32;
+            dims.w_max = wmax[k];
+            if (packed_smem_bytes(2 * k, dims) > 200 * 1024) {
+                rc = launch_general(ctx, false, d_fams, d_lists + offs[k], (long long)lists[k].size(), d_arena, d_table,
+                                    b_len, rowlen, ctx->stream);
+                if (rc) return rc;
+                continue;
+            }
+            e = launch_packed(2 * k, d_fams, d_lists + offs[k], (int)lists[k].size(), d_arena, ctx->d_consts,
+                              (int *)d_table, dims, d_fb, ctx->d_queue + 2, ctx->stream);
+            if (e != cudaSuccess) return set_err(STRK_ERR_CUDA, "%s: packed launch: %s", who, cudaGetErrorString(e));
+            ctx->stats[2] += 1;
+            n_packed += (long long)lists[k].size();
+        }
+        rc = launch_general(ctx, false, d_fams, d_lists + offs[0], (long long)lists[0].size(), d_arena, d_table, b_len,
+                            rowlen, ctx->stream);
+        if (rc) return rc;
+        if (n_packed) {
+            rc = launch_general(ctx, false, d_fams, d_fb, n_packed, d_arena, d_table, b_len, rowlen, ctx->stream,
+                                ctx->d_queue + 2);
+            if (rc) return rc;
+            unsigned int fb = 0;
+            CU(cudaMemcpyAsync(&fb, ctx->d_queue + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->stats[6] = (double)(n_packed - (long long)fb);
+        }
+        ctx->stats[7] = (double)n_reads - ctx->stats[6];
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     if (!ref) {
         CU(cudaMemcpy(out_host, d_table, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
@@ -666,9 +888,8 @@ extern "C" int strk_score_tables(strk_ctx *ctx, const uint8_t *arena, uint64_t a
                                  const int32_t *lens, const int32_t *motif_idx, const int32_t *n_lo, const int32_t *n_hi,
                                  int64_t n_reads, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_motifs,
                                  const uint64_t *out_off, int kernel, int32_t *scores) {
-    (void)kernel;
     return tables_common(ctx, false, arena, arena_bytes, seq_off, lens, motif_idx, n_lo, n_hi, n_reads, motif_off,
-                         motif_len, n_motifs, out_off, scores);
+                         motif_len, n_motifs, out_off, kernel, scores);
 }
 
 extern "C" int strk_ref_boundary_tables(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes,
@@ -676,7 +897,7 @@ extern "C" int strk_ref_boundary_tables(strk_ctx *ctx, const uint8_t *arena, uin
                                         const int32_t *n_hi, int64_t n_loci, const uint64_t *motif_off,
                                         const int32_t *motif_len, const uint64_t *out_off, int32_t *out) {
     return tables_common(ctx, true, arena, arena_bytes, seq_off, lens, nullptr, n_lo, n_hi, n_loci, motif_off, motif_len,
-                         n_loci, out_off, out);
+                         n_loci, out_off, STRK_KERNEL_GENERAL, out);
 }
 
 extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,

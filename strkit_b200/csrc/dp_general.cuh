@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(256) dp_general_kernel(const FamDesc *__restri
                                                          int n_fams, const unsigned char *__restrict__ arena,
                                                          const ScoreConsts *__restrict__ consts, void *table,
                                                          int *scratch, int scratch_rowlen, int scratch_b_len,
-                                                         unsigned int *queue) {
+                                                         unsigned int *queue,
+                                                         const unsigned int *__restrict__ n_fams_dev) {
+    if (n_fams_dev) n_fams = (int)*n_fams_dev;  // list length produced on the device (packed-kernel fallbacks)
     __shared__ SmemConsts sc;
     for (int k = threadIdx.x; k < 256; k += blockDim.x) sc.lut[k] = consts->lut[k];
     for (int k = threadIdx.x; k < STRK_SMAT_ROWS * STRK_NSYM_; k += blockDim.x) sc.smat[k] = consts->smat[k];

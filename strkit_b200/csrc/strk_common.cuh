@@ -25,7 +25,19 @@ struct ScoreConsts {
     signed char smat[STRK_SMAT_ROWS * STRK_NSYM_]; // [row symbol or pad][column symbol]
     int gap;
     int end_flags;
+    // packed kernel: PRMT byte tables per column symbol (row classes A,C,G,T,N,X,other,pad), biased by +2g;
+    // the forward (t8f) and backward (t8b) sweeps differ in the pad-row byte only
+    unsigned long long t8f[STRK_NSYM_], t8b[STRK_NSYM_];
+    unsigned char cls_of[STRK_SMAT_ROWS + 1];  // symbol code -> PRMT row class, 0x80 = not representable
+    int packed_ok;                             // every biased score fits a positive byte
 };
+
+// rows per lane of the packed kernel (even values only, 32*R >= n1); 0 = too long for it
+__host__ __device__ inline int strk_pick_rows_packed(int n1) {
+    int r = (n1 + 63) / 64 * 2;
+    if (r < 2) r = 2;
+    return r <= 16 ? r : 0;
+}
 
 __host__ __device__ inline int strk_pick_rows(int n1) {
     // rows per lane of the strip layout: smallest R in the instantiated set with 32*R >= n1

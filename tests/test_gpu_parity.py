@@ -3,7 +3,7 @@ Run on the GPU box with `pytest -m gpu`."""
 import numpy as np
 import pytest
 
-from tests.helpers import families_to_batch, oracle_tables, random_families
+from tests.helpers import families_to_batch, mutate, oracle_tables, random_families
 
 pytestmark = pytest.mark.gpu
 
@@ -16,8 +16,9 @@ def sb():
     return strkit_b200
 
 
+@pytest.mark.parametrize("kernel", ["auto", "general"])
 @pytest.mark.parametrize("flags", list(range(16)))
-def test_score_tables_all_modes_small(sb, oracle, flags):
+def test_score_tables_all_modes_small(sb, oracle, flags, kernel):
     rng = np.random.default_rng(100 + flags)
     fams = random_families(rng, 120)
     n_lo, n_hi = [], []
@@ -29,9 +30,46 @@ def test_score_tables_all_modes_small(sb, oracle, flags):
         n_lo.append(lo)
         n_hi.append(lo + int(rng.integers(0, 9)))
     eng = sb.Engine(end_flags=flags)
+    got, _ = eng.score_tables(families_to_batch(fams), np.array(n_lo), np.array(n_hi),
+                              kernel=sb.KERNEL_GENERAL if kernel == "general" else sb.KERNEL_AUTO)
+    want = oracle_tables(oracle, fams, n_lo, n_hi, flags)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    st = eng.stats()
+    if kernel == "auto":  # most of these families are eligible for the packed u16x2 kernel
+        assert st["reads_packed_kernel"] > 40 and st["reads_general_kernel"] > 0
+    else:
+        assert st["reads_packed_kernel"] == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", [0, 2, 5, 10, 15])
+def test_score_tables_packed_kernel_realistic_lengths(sb, oracle, flags):
+    """Read-sized families (db 100-510 bases, every packed R), wide windows, X / N wildcards, lower case."""
+    rng = np.random.default_rng(200 + flags)
+    fams, n_lo, n_hi = [], [], []
+    for i in range(64):
+        m = int(rng.integers(1, 9))
+        motif = "".join(rng.choice(list("ACGT"), size=m))
+        k = int(rng.integers(1, max(2, 370 // m)))
+        tr = mutate(rng, motif * k, 0.03, 0.02, 0.02)[:370]
+        fl = "".join(rng.choice(list("ACGT"), size=int(rng.integers(1, 71))))
+        fr = "".join(rng.choice(list("ACGT"), size=int(rng.integers(1, 71))))
+        if i % 3 == 0:
+            tr = "".join("X" if rng.random() < 0.03 else ("N" if rng.random() < 0.01 else ch) for ch in tr)
+            fl = "".join("X" if rng.random() < 0.03 else ch for ch in fl)
+            fr = "".join("N" if rng.random() < 0.03 else ch for ch in fr)
+        if i % 5 == 0:
+            tr, fl = tr.lower(), fl.lower()
+        e = round(len(tr) / m)
+        lo = max(0, e - int(rng.integers(0, 12)))
+        fams.append((motif, tr or "A", fl, fr))
+        n_lo.append(lo)
+        n_hi.append(lo + int(rng.integers(0, 24)))
+    eng = sb.Engine(end_flags=flags)
     got, _ = eng.score_tables(families_to_batch(fams), np.array(n_lo), np.array(n_hi))
     want = oracle_tables(oracle, fams, n_lo, n_hi, flags)
     assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    assert eng.stats()["reads_packed_kernel"] == len(fams)
     eng.close()
 
 
@@ -83,6 +121,9 @@ def test_batch_config1_bit_exact(sb, oracle):
     st = eng.stats()
     assert st["reference_cells"] == cells  # the replay scored exactly the sizes the reference scores
     assert 0 < st["executed_cells"] < cells
+    assert st["reads_packed_kernel"] == batch.n_reads  # HiFi reads all take the packed u16x2 kernel
+    got_general = eng.count_reads(batch, params, kernel=sb.KERNEL_GENERAL)
+    assert np.array_equal(got_general, want) and eng.stats()["reads_packed_kernel"] == 0
 
 
 def test_batch_noisy_ont_and_bad_estimates_force_widening(sb, oracle):
