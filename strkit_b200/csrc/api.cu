@@ -84,6 +84,7 @@ struct strk_ctx {
     DevBuf<int> list_a, list_b;      // widening-pass lists
     DevBuf<long long> list_c;
     DevBuf<int> fallback;            // reads the packed kernel handed to the general kernel
+    DevBuf<uint4> pk_scratch;        // captured DP columns of the packed kernel (per resident warp)
     unsigned int *d_queue = nullptr;  // [0] work queue, [1] miss counter
     double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -230,6 +231,7 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     ctx->list_b.release();
     ctx->list_c.release();
     ctx->fallback.release();
+    ctx->pk_scratch.release();
     if (ctx->d_consts) cudaFree(ctx->d_consts);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     if (ctx->d_acc) cudaFree(ctx->d_acc);
@@ -328,44 +330,47 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// packed DP launch (one template instantiation per R)
+// packed DP launch (one template instantiation per R; persistent warps, per-warp L2-resident scratch)
 // ------------------------------------------------------------------------------------------------
-static const int PK_WARPS = 4;
-
-static size_t packed_smem_bytes(int R, const PackedSmemDims &d) {
-    const int fcol_words = d.w_max * (R / 2) * 32, bq_words = (R / 2) * 32;
-    const int per_warp16 = d.colt_entries + (d.prof_words + fcol_words + bq_words + 2 * d.w_max + 3) / 4 + 1;
-    return (size_t)per_warp16 * 16 * PK_WARPS;
-}
-
 template <int R>
-static cudaError_t launch_packed_r(const FamDesc *fams, const int *list, int n, const unsigned char *arena,
-                                   const ScoreConsts *consts, int *table, PackedSmemDims dims, int *fb_list,
-                                   unsigned int *fb_count, cudaStream_t st) {
-    const size_t smem = packed_smem_bytes(R, dims);
+static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
+                           int *table, PackedDims dims, cudaStream_t st) {
+    const size_t smem = pk_smem_bytes(R, dims);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        CU(cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dp_packed_kernel<R><<<(n + PK_WARPS - 1) / PK_WARPS, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, consts, table, dims,
-                                                                                     fb_list, fb_count);
-    return cudaGetLastError();
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_packed_kernel<R>, PK_WARPS * 32, smem));
+    if (per_sm < 1) return set_err(STRK_ERR_CUDA, "packed kernel R=%d does not fit an SM (%zu B shared)", R, smem);
+    long long grid = (long long)per_sm * ctx->n_sm;
+    const long long need = ((long long)n + PK_WARPS - 1) / PK_WARPS;
+    if (grid > need) grid = need;
+    const size_t words = pk_scratch_words_per_warp(R, dims.w_max) * (size_t)grid * PK_WARPS;
+    if (ctx->pk_scratch.reserve((words + 3) / 4) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", words * 4);
+    }
+    dp_packed_kernel<R><<<(unsigned)grid, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
+                                                                     ctx->pk_scratch.p, ctx->fallback.p,
+                                                                     ctx->d_queue + 2);
+    CU(cudaGetLastError());
+    ctx->stats[2] += 1;
+    return STRK_OK;
 }
 
-static cudaError_t launch_packed(int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
-                                 const ScoreConsts *consts, int *table, PackedSmemDims dims, int *fb_list,
-                                 unsigned int *fb_count, cudaStream_t st) {
+static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
+                         int *table, PackedDims dims, cudaStream_t st) {
     switch (R) {
-        case 2: return launch_packed_r<2>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        case 4: return launch_packed_r<4>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        case 6: return launch_packed_r<6>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        case 8: return launch_packed_r<8>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        case 10: return launch_packed_r<10>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        case 12: return launch_packed_r<12>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        case 14: return launch_packed_r<14>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
-        default: return launch_packed_r<16>(fams, list, n, arena, consts, table, dims, fb_list, fb_count, st);
+        case 2: return launch_packed_r<2>(ctx, fams, list, n, arena, table, dims, st);
+        case 4: return launch_packed_r<4>(ctx, fams, list, n, arena, table, dims, st);
+        case 6: return launch_packed_r<6>(ctx, fams, list, n, arena, table, dims, st);
+        case 8: return launch_packed_r<8>(ctx, fams, list, n, arena, table, dims, st);
+        case 10: return launch_packed_r<10>(ctx, fams, list, n, arena, table, dims, st);
+        case 12: return launch_packed_r<12>(ctx, fams, list, n, arena, table, dims, st);
+        case 14: return launch_packed_r<14>(ctx, fams, list, n, arena, table, dims, st);
+        default: return launch_packed_r<16>(ctx, fams, list, n, arena, table, dims, st);
     }
 }
 
@@ -448,7 +453,7 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
         for (int64_t r = 0; r < n_reads; ++r) {
             const int fl = lens[3 * r], fr = lens[3 * r + 2], n1 = fl + lens[3 * r + 1] + fr;
             const int m = motif_len[(size_t)b->h_read_locus[(size_t)r]];
-            int R = ctx->h_consts.packed_ok ? strk_pick_rows_packed(n1) : 0;
+            int R = ctx->h_consts.packed_ok ? strk_pick_rows_packed(n1 + 1) : 0;
             if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128) R = 0;
             bin[(size_t)r] = (unsigned char)(R / 2);
             cnt[R / 2]++;
@@ -595,22 +600,20 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             for (int k = 8; k >= 1; --k) {
                 if (!b->bin_cnt[k]) continue;
                 const int R = 2 * k;
-                PackedSmemDims dims;
-                dims.colt_entries = b->bin_flank[k] + 32;
+                PackedDims dims;
+                dims.colt_entries = b->bin_flank[k] + 64;
                 dims.prof_words = b->bin_mmax[k] * R * 32;
                 dims.w_max = W;
-                cudaError_t e = cudaSuccess;
-                if (packed_smem_bytes(R, dims) > 200 * 1024) {
+                if (pk_smem_bytes(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
                     rc = launch_general(ctx, false, ctx->fams.p, b->d_order + b->bin_off[k], b->bin_cnt[k], b->d_arena,
                                         ctx->table.p, b_len, rowlen, st);
                     if (rc) return rc;
                     continue;
                 }
-                e = launch_packed(R, ctx->fams.p, b->d_order + b->bin_off[k], (int)b->bin_cnt[k], b->d_arena, ctx->d_consts,
-                                  ctx->table.p, dims, ctx->fallback.p, ctx->d_queue + 2, st);
-                if (e != cudaSuccess) return set_err(STRK_ERR_CUDA, "packed kernel launch (R=%d): %s", R, cudaGetErrorString(e));
-                ctx->stats[2] += 1;
+                rc = launch_packed(ctx, R, ctx->fams.p, b->d_order + b->bin_off[k], (int)b->bin_cnt[k], b->d_arena,
+                                   ctx->table.p, dims, st);
+                if (rc) return rc;
                 n_packed += b->bin_cnt[k];
             }
             rc = launch_general(ctx, false, ctx->fams.p, b->d_order, b->n_general, b->d_arena, ctx->table.p, b_len, rowlen, st);
@@ -807,7 +810,7 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
         int mmax[9] = {0}, flank[9] = {0}, wmax[9] = {0};
         for (int64_t r = 0; r < n_reads; ++r) {
             const FamDesc &f = fams[(size_t)r];
-            int R = strk_pick_rows_packed(f.n_fl + f.n_tr + f.n_fr);
+            int R = strk_pick_rows_packed(f.n_fl + f.n_tr + f.n_fr + 1);
             if (f.n_fl < 1 || f.n_fr < 1 || f.n_fl > PK_FLANK_MAX || f.n_fr > PK_FLANK_MAX || f.m * R > 128 ||
                 f.n_hi - f.n_lo + 1 > 64)
                 R = 0;
@@ -822,28 +825,28 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
             offs[k] = flat.size();
             flat.insert(flat.end(), lists[k].begin(), lists[k].end());
         }
-        int *d_lists = nullptr, *d_fb = nullptr;
+        int *d_lists = nullptr;
         e = tmp.up(&d_lists, flat.data(), flat.size());
-        if (e == cudaSuccess) e = tmp.up(&d_fb, (const int *)nullptr, (size_t)n_reads);
+        if (e == cudaSuccess) e = ctx->fallback.reserve((size_t)n_reads);
+        int *d_fb = ctx->fallback.p;
         if (e != cudaSuccess) return set_err(STRK_ERR_NOMEM, "%s: %s", who, cudaGetErrorString(e));
         CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), ctx->stream));
         long long n_packed = 0;
         for (int k = 8; k >= 1; --k) {
             if (lists[k].empty()) continue;
-            PackedSmemDims dims;
-            dims.colt_entries = flank[k] + 32;
+            PackedDims dims;
+            dims.colt_entries = flank[k] + 64;
             dims.prof_words = mmax[k] * 2 * k * 32;
             dims.w_max = wmax[k];
-            if (packed_smem_bytes(2 * k, dims) > 200 * 1024) {
+            if (pk_smem_bytes(2 * k, dims) > 200 * 1024) {
                 rc = launch_general(ctx, false, d_fams, d_lists + offs[k], (long long)lists[k].size(), d_arena, d_table,
                                     b_len, rowlen, ctx->stream);
                 if (rc) return rc;
                 continue;
             }
-            e = launch_packed(2 * k, d_fams, d_lists + offs[k], (int)lists[k].size(), d_arena, ctx->d_consts,
-                              (int *)d_table, dims, d_fb, ctx->d_queue + 2, ctx->stream);
-            if (e != cudaSuccess) return set_err(STRK_ERR_CUDA, "%s: packed launch: %s", who, cudaGetErrorString(e));
-            ctx->stats[2] += 1;
+            rc = launch_packed(ctx, 2 * k, d_fams, d_lists + offs[k], (int)lists[k].size(), d_arena, (int *)d_table, dims,
+                               ctx->stream);
+            if (rc) return rc;
             n_packed += (long long)lists[k].size();
         }
         rc = launch_general(ctx, false, d_fams, d_lists + offs[0], (long long)lists[0].size(), d_arena, d_table, b_len,

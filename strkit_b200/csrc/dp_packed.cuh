@@ -1,4 +1,4 @@
-// dp_packed.cuh -- packed u16x2 DPX kernel for the bulk of the reads (db <= 512 bases).
+// dp_packed.cuh -- packed u16x2 DPX kernel for the bulk of the reads (db < 512 bases).
 //
 // Same strip wavefront as dp_general.cuh (lane t owns R consecutive rows of db, columns swept with a
 // one-column skew per lane, bottom cell handed down with __shfl_up_sync), but every 32-bit lane word
@@ -22,8 +22,15 @@
 //     period m, so a packed query profile prof[k][row] is built once per read in shared memory and the
 //     step costs LDS + IADD + VIMNMX3 per cell pair.  The candidate is never materialised.
 //
-// Rows are front-padded to 32*R with a pad class whose score reproduces the border row (see
-// dp_general.cuh), so row n1 is always the last register of the last lane.
+// The step loops are branch-free.  Lanes that have not started yet (column <= 0) run on an all-zero score
+// table, which leaves their border column untouched (the biased borders are non-decreasing down the rows);
+// lanes that are past the last column compute values nobody reads.  Candidate columns (and the final column
+// of the backward half) are captured with predicated 128-bit stores into a per-warp scratch that stays in
+// L2; the combine pass reads them back.
+//
+// Rows are front-padded to 32*R (> n1, so there is always at least one pad row, which doubles as DP row 0)
+// with a pad class whose score reproduces the border row (see dp_general.cuh); row n1 is therefore always
+// the last register of lane 31.
 //
 // Reads this kernel cannot take (IUPAC codes inside the read, value range beyond u16, empty flank) are
 // appended to a fallback list that the general int32 kernel processes afterwards -- still on the GPU.
@@ -32,14 +39,22 @@
 #include "strk_common.cuh"
 
 #define PK_FLANK_MAX 160  // longest flank the packed kernel stages (reference default flank_size = 70)
+#define PK_WARPS 4        // warps (= reads in flight) per CTA
 
-struct PackedSmemDims {
-    int colt_entries;  // uint4 entries of the per-column table  (>= max flank + 32)
+struct PackedDims {
+    int colt_entries;  // uint4 entries of the per-column table  (>= max flank + 64)
     int prof_words;    // u32 words of the packed profile        (>= m_max * R * 32)
-    int w_max;         // candidate sizes per read               (table row stride)
+    int w_max;         // candidate sizes per read
 };
 
-__device__ __forceinline__ unsigned pk_vimax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
+__host__ __device__ inline int pk_quads(int R) { return (R + 1 + 3) / 4; }  // H[0..R) + the prefix-max word
+__host__ __device__ inline size_t pk_scratch_words_per_warp(int R, int w_max) {
+    return (size_t)(w_max + 1) * pk_quads(R) * 32 * 4;
+}
+__host__ __device__ inline size_t pk_smem_bytes(int R, const PackedDims &d) {
+    (void)R;
+    return ((size_t)d.colt_entries * 16 + (size_t)d.prof_words * 4 + 15) / 16 * 16 * PK_WARPS;
+}
 
 // Raw PRMT (generic mode).  NOT __byte_perm: that intrinsic masks the selector with 0x7777, which costs an
 // extra LOP and drops bit 3 of each nibble -- the sign-replicate bit used here to produce the zero bytes.
@@ -50,13 +65,14 @@ __device__ __forceinline__ unsigned pk_prmt(unsigned a, unsigned b, unsigned sel
 }
 
 template <int R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PK_WARPS * 32)
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
-                 int *__restrict__ table, PackedSmemDims dims, int *__restrict__ fallback_list,
-                 unsigned int *__restrict__ fallback_count) {
+                 int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
+                 int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count) {
     static_assert(R % 2 == 0 && R >= 2 && R <= 16, "R must be even");
     constexpr int N = 32 * R;
+    constexpr int QN = (R + 1 + 3) / 4;
     extern __shared__ uint4 smem_raw[];
     __shared__ SmemConsts sc;
     __shared__ unsigned long long t8f[STRK_NSYM_], t8b[STRK_NSYM_];
@@ -72,235 +88,285 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int fam_idx = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (fam_idx >= n_list) return;
-    const int fam_id = list[fam_idx];
-    const FamDesc f = fams[fam_id];
+    const int warp_global = blockIdx.x * PK_WARPS + warp;
+    const int total_warps = gridDim.x * PK_WARPS;
     const int g = consts->gap;
     const int flags = consts->end_flags;
     const bool s1_beg = flags & 1, s1_end = flags & 2, s2_beg = flags & 4, s2_end = flags & 8;
+    const bool lane0 = lane == 0;
 
-    // per-warp shared memory carve-up (16-byte units)
-    const int fcol_words = dims.w_max * (R / 2) * 32;
-    const int bq_words = (R / 2) * 32;
-    const int per_warp16 = dims.colt_entries + (dims.prof_words + fcol_words + bq_words + 2 * dims.w_max + 3) / 4 + 1;
-    uint4 *colT = smem_raw + (size_t)warp * per_warp16;
+    const size_t smem16 = ((size_t)dims.colt_entries * 16 + (size_t)dims.prof_words * 4 + 15) / 16;
+    uint4 *colT = smem_raw + (size_t)warp * smem16;  // entry [j + 31] for columns j = -31 .. Lmax + 31
     unsigned *prof = (unsigned *)(colT + dims.colt_entries);
-    unsigned *fcols = prof + dims.prof_words;
-    unsigned *bq = fcols + fcol_words;
-    unsigned *flast = bq + bq_words;  // [w_max] last-row prefix maxima at the candidate columns
-
-    const int n1 = f.n_fl + f.n_tr + f.n_fr;
-    const int off = N - n1;
-    const int m = f.m;
-    const unsigned char *db = arena + f.db_off;
-    const unsigned char *motif = arena + f.motif_off;
-
-    // split of the tract: b0 copies go to the backward half
-    int b0 = (m * f.n_hi + f.n_fl - f.n_fr + m) / (2 * m);
-    b0 = b0 < 0 ? 0 : (b0 > f.n_lo ? f.n_lo : b0);
-    const int a_lo = f.n_lo - b0, a_hi = f.n_hi - b0;
-    const int nW = a_hi - a_lo + 1;
-    const int colsF = f.n_fl + m * a_hi, colsB = f.n_fr + m * b0;
-    const int ncols = colsF > colsB ? colsF : colsB;
-    const int Lmax = f.n_fl > f.n_fr ? f.n_fl : f.n_fr;
-
-    // ---- eligibility (warp-uniform): anything odd goes to the general kernel
-    bool ok = n1 <= N && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 32 <= dims.colt_entries &&
-              m * R * 32 <= dims.prof_words && nW <= dims.w_max && (g * (N + ncols + 2) + 2 * N + 256) < 65535;
-    // row symbols
-    int codeFB[R];  // forward code | backward code << 8   (setup only)
-    unsigned selF[R], selB[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
-        int cf = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, cb = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
-        if (i >= 1 && i <= n1) {
-            cf = sc.lut[db[i - 1]];
-            cb = sc.lut[db[n1 - i]];
-        }
-        codeFB[r] = cf | (cb << 8);
-        const unsigned kf = cls_of[cf], kb = cls_of[cb];
-        if ((kf | kb) & 0x80) ok = false;
-        selF[r] = (kf & 7) | 0x8880u;
-        selB[r] = ((kb & 7) << 8) | 0x8088u;
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    if (!ok) {
-        if (lane == 0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
-        return;
-    }
-
-    // ---- per-column PRMT tables for the flank phase (columns 1 .. Lmax + 31)
-    const int ct_n = Lmax + 31 < ncols ? Lmax + 31 : ncols;
-    for (int j = lane + 1; j <= ct_n; j += 32) {
-        int sf, sb;
-        if (j <= f.n_fl)
-            sf = sc.lut[db[j - 1]];
-        else
-            sf = sc.lut[motif[(j - f.n_fl - 1) % m]];
-        if (j <= f.n_fr)
-            sb = sc.lut[db[n1 - j]];
-        else
-            sb = sc.lut[motif[m - 1 - (j - f.n_fr - 1) % m]];
-        const unsigned long long a = t8f[sf], b = t8b[sb];
-        colT[j] = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
-    }
-    // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
-    const int g2 = 2 * g;
-    for (int k = 0; k < m; ++k) {
-        const int sf = sc.lut[motif[(k + Lmax - f.n_fl) % m]];
-        const int sb = sc.lut[motif[m - 1 - (k + Lmax - f.n_fr) % m]];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int vf = sc.smat[(codeFB[r] & 0xff) * STRK_NSYM_ + sf] + g2;
-            const int vb = sc.smat[(codeFB[r] >> 8) * STRK_NSYM_ + sb] + g2;
-            prof[(k * R + r) * 32 + lane] = (unsigned)vf | ((unsigned)vb << 16);
-        }
-    }
-    for (int k = lane; k < bq_words; k += 32) bq[k] = 0u;
-
-    // ---- borders (biased by g * (row + col))
-    unsigned H[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int I = lane * R + r + 1, i = I - off;
-        int bf = 0, bb = 0;  // unbiased column-0 values
-        if (i >= 1) {
-            bf = s1_beg ? 0 : -g * i;
-            bb = s1_end ? (i == n1 ? -g : 0) : -g * i;
-        }
-        H[r] = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
-    }
-    unsigned prev_up;
-    {
-        const int I = lane * R, i = I - off;
-        int bf = 0, bb = 0;
-        if (i >= 1) {
-            bf = s1_beg ? 0 : -g * i;
-            bb = s1_end ? 0 : -g * i;  // i < n1 here
-        }
-        prev_up = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
-    }
+    uint4 *scr = scratch + (size_t)warp_global * (size_t)(dims.w_max + 1) * QN * 32;
     const unsigned tinc = (s2_beg ? (unsigned)g : 0u) | ((s2_end ? (unsigned)g : 0u) << 16);
     const unsigned ginc = (unsigned)g | ((unsigned)g << 16);
-    unsigned topv = 0u;  // top border at the column lane 0 is about to compute
-    unsigned pm = 0u;    // biased prefix maxima of the last row (both halves), lane 31
-    int next_cand = f.n_fl + m * a_lo, w = 0;
-    unsigned bextra = 0u, bq_top = 0u;
-    __syncwarp();
+    const int g2 = 2 * g;
 
-    const int nsteps = ncols + 31;
-    const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first step of the motif phase (warp-uniform)
+    for (int fam_idx = warp_global; fam_idx < n_list; fam_idx += total_warps) {
+        const int fam_id = list[fam_idx];
+        const FamDesc f = fams[fam_id];
+        const int n1 = f.n_fl + f.n_tr + f.n_fr;
+        const int off = N - n1;
+        const int m = f.m;
+        const unsigned char *db = arena + f.db_off;
+        const unsigned char *motif = arena + f.motif_off;
 
-    // candidate-column / final-column bookkeeping shared by both phases
-#define PK_STEP_TAIL()                                                                                         \
-    pm = (j == 1) ? H[R - 1] : __viaddmax_u16x2(pm, ginc, H[R - 1]);                                           \
-    if (j == next_cand) {                                                                                      \
-        _Pragma("unroll") for (int q = 0; q < R / 2; ++q)                                                      \
-            fcols[(w * (R / 2) + q) * 32 + lane] = __byte_perm(H[2 * q], H[2 * q + 1], 0x5410);                \
-        if (lane == 31) flast[w] = pm & 0xffffu;                                                               \
-        ++w;                                                                                                   \
-        next_cand = w < nW ? next_cand + m : 0x7fffffff;                                                       \
-    }                                                                                                          \
-    if (j == colsB) {                                                                                          \
-        _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                        \
-            const int Ib = lane * R + r + 1;                                                                   \
-            const int If = N + off - Ib; /* forward row paired with this backward row */                       \
-            if (Ib >= off && If >= 1) {                                                                        \
-                const int lf = (If - 1) / R, rf = (If - 1) % R;                                                \
-                ((unsigned short *)bq)[((rf >> 1) * 32 + lf) * 2 + (rf & 1)] = (unsigned short)(H[r] >> 16);   \
-            }                                                                                                  \
-        }                                                                                                      \
-        if (lane == 31) {                                                                                      \
-            bextra = pm >> 16;                                                                                 \
-            bq_top = H[R - 1] >> 16;                                                                           \
-        }                                                                                                      \
-    }
+        // split of the tract: b0 copies go to the backward half
+        int b0 = (m * f.n_hi + f.n_fl - f.n_fr + m) / (2 * m);
+        b0 = b0 < 0 ? 0 : (b0 > f.n_lo ? f.n_lo : b0);
+        const int a_lo = f.n_lo - b0, a_hi = f.n_hi - b0;
+        const int nW = a_hi - a_lo + 1;
+        const int colsF = f.n_fl + m * a_hi, colsB = f.n_fr + m * b0;
+        const int ncols = colsF > colsB ? colsF : colsB;
+        const int Lmax = f.n_fl > f.n_fr ? f.n_fl : f.n_fr;
 
-    int s = 0;
-    // ---- flank phase: PRMT look-ups
-    for (; s < s_star; ++s) {
-        const int j = s - lane + 1;
-        unsigned up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
-        if (lane == 0) {
-            topv += tinc;
-            up_in = topv;
+        // ---- eligibility (warp-uniform): anything odd goes to the general kernel
+        bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 64 <= dims.colt_entries &&
+                  m * R * 32 <= dims.prof_words && nW <= dims.w_max && (g * (N + ncols + 40) + 2 * N + 1024) < 65535;
+        int codeFB[R];  // forward code | backward code << 8   (setup only)
+        unsigned selF[R], selB[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
+            int cf = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, cb = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
+            if (i >= 1 && i <= n1) {
+                cf = sc.lut[db[i - 1]];
+                cb = sc.lut[db[n1 - i]];
+            }
+            codeFB[r] = cf | (cb << 8);
+            const unsigned kf = cls_of[cf], kb = cls_of[cb];
+            if ((kf | kb) & 0x80) ok = false;
+            selF[r] = (kf & 7) | 0x8880u;
+            selB[r] = ((kb & 7) << 8) | 0x8088u;
         }
-        if (j >= 1 && j <= ncols) {
-            const uint4 ct = colT[j];
-            unsigned d = prev_up, u = up_in;
-            prev_up = up_in;
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) {
+            if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
+            continue;
+        }
+        __syncwarp();  // previous family's readers of colT / prof are done
+
+        // ---- per-column PRMT tables for the flank phase: columns -31 .. Lmax + 31 (zero tables for j <= 0)
+        for (int e = lane; e <= Lmax + 62; e += 32) {
+            const int j = e - 31;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (j >= 1) {
+                int sf, sb;
+                if (j <= f.n_fl)
+                    sf = sc.lut[db[j - 1]];
+                else
+                    sf = sc.lut[motif[(j - f.n_fl - 1) % m]];
+                if (j <= f.n_fr)
+                    sb = sc.lut[db[n1 - j]];
+                else
+                    sb = sc.lut[motif[m - 1 - (j - f.n_fr - 1) % m]];
+                const unsigned long long a = t8f[sf], b = t8b[sb];
+                v = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+            }
+            colT[e] = v;
+        }
+        // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
+        for (int k = 0; k < m; ++k) {
+            const int sf = sc.lut[motif[(k + Lmax - f.n_fl) % m]];
+            const int sb = sc.lut[motif[m - 1 - (k + Lmax - f.n_fr) % m]];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const unsigned left = H[r];
-                const unsigned t = d + pk_prmt(ct.x, ct.y, selF[r]) + pk_prmt(ct.z, ct.w, selB[r]);
-                const unsigned h = pk_vimax3(t, u, left);
-                d = left;
-                u = h;
-                H[r] = h;
+                const int vf = sc.smat[(codeFB[r] & 0xff) * STRK_NSYM_ + sf] + g2;
+                const int vb = sc.smat[(codeFB[r] >> 8) * STRK_NSYM_ + sb] + g2;
+                prof[(k * R + r) * 32 + lane] = (unsigned)vf | ((unsigned)vb << 16);
             }
-            PK_STEP_TAIL()
         }
-    }
-    // ---- motif phase: packed profile from shared memory
-    int k = 0;
-    {
-        const int j = s - lane + 1;  // >= Lmax + 1 for every lane here
-        k = (j - Lmax - 1) % m;
-        if (k < 0) k += m;
-    }
-    for (; s < nsteps; ++s) {
-        const int j = s - lane + 1;
-        unsigned up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
-        if (lane == 0) {
-            topv += tinc;
-            up_in = topv;
-        }
-        if (j <= ncols) {
-            const unsigned *pp = prof + k * (R * 32) + lane;
-            unsigned d = prev_up, u = up_in;
-            prev_up = up_in;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const unsigned left = H[r];
-                const unsigned t = d + pp[r * 32];
-                const unsigned h = pk_vimax3(t, u, left);
-                d = left;
-                u = h;
-                H[r] = h;
-            }
-            PK_STEP_TAIL()
-        }
-        k = k + 1 == m ? 0 : k + 1;
-    }
-#undef PK_STEP_TAIL
 
-    // ---- combine: score(n) for every candidate of the window
-    bextra = __shfl_sync(0xffffffffu, bextra, 31);
-    bq_top = __shfl_sync(0xffffffffu, bq_top, 31);
-    __syncwarp();
-    int *out = table + f.out_off;
-    for (int ww = 0; ww < nW; ++ww) {
-        unsigned acc = 0u;
+        // ---- borders (biased by g * (row + col))
+        unsigned H[R];
 #pragma unroll
-        for (int q = 0; q < R / 2; ++q)
-            acc = __viaddmax_u16x2(fcols[(ww * (R / 2) + q) * 32 + lane], bq[q * 32 + lane], acc);
-        unsigned v = max(acc & 0xffffu, acc >> 16);
-        v = __reduce_max_sync(0xffffffffu, v);
-        if (lane == 0) {
-            const int p = f.n_fl + m * (a_lo + ww);
-            int best = (int)v - g * (N + off + p + colsB);
-            if (off == 0) {  // forward row 0 is the top border, not a stored row
-                const int f0 = s2_beg ? 0 : -g * p;
-                best = max(best, f0 + (int)bq_top - g * (N + colsB));
+        for (int r = 0; r < R; ++r) {
+            const int I = lane * R + r + 1, i = I - off;
+            int bf = 0, bb = 0;  // unbiased column-0 values
+            if (i >= 1) {
+                bf = s1_beg ? 0 : -g * i;
+                bb = s1_end ? (i == n1 ? -g : 0) : -g * i;
             }
-            if (s2_end) best = max(best, (int)flast[ww] - g * (N + p));
-            if (s2_beg) {
-                const int border = s1_end ? -g : -g * n1;  // backward cell (n1, 0)
-                best = max(best, max((int)bextra - g * (N + colsB), border));
-            }
-            out[a_lo + ww + b0 - f.n_lo] = best;
+            H[r] = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
         }
+        unsigned prev_up;
+        {
+            const int I = lane * R, i = I - off;
+            int bf = 0, bb = 0;
+            if (i >= 1) {
+                bf = s1_beg ? 0 : -g * i;
+                bb = s1_end ? 0 : -g * i;  // i < n1 here
+            }
+            prev_up = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
+        }
+        unsigned topv = 0u;  // top border of the column lane 0 computes next
+        unsigned pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
+        int next_cand = f.n_fl + m * a_lo, w = 0, bslot = nW;
+        int j = 1 - lane;  // column this lane computes in the current step
+        __syncwarp();
+
+        const int nsteps = ncols + 31;
+        const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first motif-phase step (warp-uniform)
+        const int first_evt = next_cand < colsB ? next_cand : colsB;  // first captured column; lane 0 is there at
+        const int s_cap = first_evt - 1;                              // step first_evt - 1
+
+#define PK_PROLOGUE()                                                 \
+    unsigned up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);        \
+    topv += tinc;                                                     \
+    up_in = lane0 ? topv : up_in;                                     \
+    unsigned d = prev_up, u = up_in;                                  \
+    prev_up = up_in;
+
+#define PK_CORE_FLANK()                                                                                     \
+    {                                                                                                       \
+        const uint4 ct = colT[j + 31];                                                                      \
+        _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                     \
+            const unsigned left = H[r];                                                                     \
+            const unsigned t = d + pk_prmt(ct.x, ct.y, selF[r]) + pk_prmt(ct.z, ct.w, selB[r]);             \
+            const unsigned h = __vimax3_u16x2(t, u, left);                                                  \
+            d = left;                                                                                       \
+            u = h;                                                                                          \
+            H[r] = h;                                                                                       \
+        }                                                                                                   \
+    }
+
+#define PK_CORE_PROF()                                                                                      \
+    {                                                                                                       \
+        const unsigned *pp = prof + k * (R * 32) + lane;                                                    \
+        _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                     \
+            const unsigned left = H[r];                                                                     \
+            const unsigned t = d + pp[r * 32];                                                              \
+            const unsigned h = __vimax3_u16x2(t, u, left);                                                  \
+            d = left;                                                                                       \
+            u = h;                                                                                          \
+            H[r] = h;                                                                                       \
+        }                                                                                                   \
+        k = k + 1 == m ? 0 : k + 1;                                                                         \
+    }
+
+// capture of candidate columns (forward half) and of the final backward column: predicated 128-bit stores
+#define PK_CAPTURE()                                                                                        \
+    {                                                                                                       \
+        const bool c1 = j == next_cand, c2 = j == colsB;                                                    \
+        if (c1 | c2) {                                                                                      \
+            const int slot = c1 ? w : nW;                                                                   \
+            uint4 *dst = scr + (size_t)slot * (QN * 32) + lane;                                             \
+            _Pragma("unroll") for (int q = 0; q < QN; ++q) {                                                \
+                uint4 v;                                                                                    \
+                v.x = 4 * q + 0 < R ? H[(4 * q + 0) % R] : pm;                                              \
+                v.y = 4 * q + 1 < R ? H[(4 * q + 1) % R] : pm;                                              \
+                v.z = 4 * q + 2 < R ? H[(4 * q + 2) % R] : pm;                                              \
+                v.w = 4 * q + 3 < R ? H[(4 * q + 3) % R] : pm;                                              \
+                dst[q * 32] = v;                                                                            \
+            }                                                                                               \
+            if (c2) bslot = slot;                                                                           \
+            if (c1) {                                                                                       \
+                ++w;                                                                                        \
+                next_cand = w < nW ? next_cand + m : 0x7fffffff;                                            \
+            }                                                                                               \
+        }                                                                                                   \
+    }
+
+#define PK_EPILOGUE()                                  \
+    pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);         \
+    ++j;
+
+        int s = 0;
+        // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
+        // maximum of the last row starts from scratch.
+        {
+            const int e1 = s_star < 31 ? s_star : 31;
+            for (; s < e1; ++s) {
+                PK_PROLOGUE()
+                PK_CORE_FLANK()
+                pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);
+                if (s >= s_cap) PK_CAPTURE()
+                ++j;
+            }
+            pm = 0u;
+            if (s_cap >= s_star) {
+                for (; s < s_star; ++s) {
+                    PK_PROLOGUE()
+                    PK_CORE_FLANK()
+                    PK_EPILOGUE()
+                }
+            } else {
+                for (; s < s_star; ++s) {
+                    PK_PROLOGUE()
+                    PK_CORE_FLANK()
+                    pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);
+                    if (s >= s_cap) PK_CAPTURE()
+                    ++j;
+                }
+            }
+        }
+        // ---- motif phase (packed profile from shared memory)
+        if (s < nsteps) {
+            int k = (j - Lmax - 1) % m;  // j >= Lmax + 1 on every lane here
+            const int e2 = s_cap < nsteps ? (s_cap > s ? s_cap : s) : nsteps;
+            for (; s < e2; ++s) {
+                PK_PROLOGUE()
+                PK_CORE_PROF()
+                PK_EPILOGUE()
+            }
+            for (; s < nsteps; ++s) {
+                PK_PROLOGUE()
+                PK_CORE_PROF()
+                pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);
+                PK_CAPTURE()
+                ++j;
+            }
+        }
+#undef PK_PROLOGUE
+#undef PK_CORE_FLANK
+#undef PK_CORE_PROF
+#undef PK_CAPTURE
+#undef PK_EPILOGUE
+
+        // ---- combine: score(n) for every candidate of the window
+        bslot = __shfl_sync(0xffffffffu, bslot, 0);
+        __syncwarp();
+        const unsigned *scw = (const unsigned *)scr;
+        unsigned Bv[R];  // backward value paired with each forward row (low half), 0 for pad rows
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int If = lane * R + r + 1;
+            unsigned v = 0u;
+            if (If >= off) {
+                const int Ib = N + off - If;  // in [off, N]
+                const int lb = (Ib - 1) / R, rb = (Ib - 1) % R;
+                v = scw[(((size_t)bslot * QN + (rb >> 2)) * 32 + lb) * 4 + (rb & 3)] >> 16;
+            }
+            Bv[r] = v;
+        }
+        const int bextra = (int)(scw[(((size_t)bslot * QN + (R >> 2)) * 32 + 31) * 4 + (R & 3)] >> 16);
+        int *out = table + f.out_off;
+        for (int ww = 0; ww < nW; ++ww) {
+            unsigned acc = 0u;
+#pragma unroll
+            for (int q = 0; q < QN; ++q) {
+                const uint4 v = scr[((size_t)ww * QN + q) * 32 + lane];
+                if (4 * q + 0 < R) acc = __viaddmax_u16x2(v.x, Bv[(4 * q + 0) % R], acc);
+                if (4 * q + 1 < R) acc = __viaddmax_u16x2(v.y, Bv[(4 * q + 1) % R], acc);
+                if (4 * q + 2 < R) acc = __viaddmax_u16x2(v.z, Bv[(4 * q + 2) % R], acc);
+                if (4 * q + 3 < R) acc = __viaddmax_u16x2(v.w, Bv[(4 * q + 3) % R], acc);
+            }
+            unsigned v = __reduce_max_sync(0xffffffffu, acc & 0xffffu);
+            if (lane0) {
+                const int p = f.n_fl + m * (a_lo + ww);
+                int best = (int)v - g * (N + off + p + colsB);
+                if (s2_end) {
+                    const int flast = (int)(scw[(((size_t)ww * QN + (R >> 2)) * 32 + 31) * 4 + (R & 3)] & 0xffffu);
+                    best = max(best, flast - g * (N + p));
+                }
+                if (s2_beg) {
+                    const int border = s1_end ? -g : -g * n1;  // backward cell (n1, 0)
+                    best = max(best, max(bextra - g * (N + colsB), border));
+                }
+                out[ww] = best;
+            }
+        }
+        __syncwarp();
     }
 }
