@@ -204,6 +204,11 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
         ctx->h_consts.cls_of[STRK_PAD_FREE] = 7;
         ctx->h_consts.cls_of[STRK_PAD_PEN] = 7;
         ctx->h_consts.packed_ok = ok;
+        int one = 1;  // one-table flank path: a non-ACGT row symbol must score the same against A, C, G and T
+        for (int c = 4; c < 7; ++c)
+            for (int b = 1; b < 4; ++b)
+                if (matrix[class_code[c] * STRK_NSYM + b] != matrix[class_code[c] * STRK_NSYM]) one = 0;
+        ctx->h_consts.one_table_ok = one;
     }
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&ctx->d_consts, sizeof(ScoreConsts)));

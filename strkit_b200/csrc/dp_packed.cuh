@@ -64,8 +64,102 @@ __device__ __forceinline__ unsigned pk_prmt(unsigned a, unsigned b, unsigned sel
     return r;
 }
 
+// Per-lane state of one read in flight.  Everything is indexed with compile-time constants after unrolling,
+// so the arrays live in registers.
 template <int R>
-__global__ void __launch_bounds__(PK_WARPS * 32)
+struct PkState {
+    unsigned H[R];     // DP cells of my R rows at the current column: forward (low) | backward (high) half
+    unsigned selA[R];  // PRMT selector (two-table path: forward half; one-table path: both halves)
+    unsigned selB[R];  // two-table path: PRMT selector of the backward half; one-table path: packed addend
+    unsigned prev_up, topv, pm;
+    int j, k, next_cand;
+    uint4 *dstF;  // next forward capture slot (lane-offset applied)
+};
+
+// FLANK1R = one-table path during the ramp-up steps: lanes that have not reached column 1 yet must see a
+// zero score, so their addend is masked off
+enum { PK_CORE_FLANK2 = 0, PK_CORE_FLANK1 = 1, PK_CORE_PROF = 2, PK_CORE_FLANK1R = 3 };
+
+// Steps [s, s_end) of the wavefront.  CORE selects the score source, FC / BC switch the predicated captures of
+// forward candidate columns / of the final backward column on.
+template <int R, int CORE, bool FC, bool BC>
+__device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, const bool lane0, const int lane,
+                                       const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ colT,
+                                       const unsigned *__restrict__ prof, const int m, const int colsF,
+                                       const int colsB, uint4 *__restrict__ dstB) {
+    constexpr int QN = (R + 1 + 3) / 4;
+#pragma unroll 1
+    for (; s < s_end; ++s) {
+        unsigned up_in = __shfl_up_sync(0xffffffffu, st.H[R - 1], 1);
+        st.topv += tinc;
+        up_in = lane0 ? st.topv : up_in;
+        unsigned d = st.prev_up, u = up_in;
+        st.prev_up = up_in;
+        if (CORE == PK_CORE_PROF) {
+            const unsigned *pp = prof + st.k * (R * 32) + lane;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned left = st.H[r];
+                const unsigned h = __vimax3_u16x2(d + pp[r * 32], u, left);
+                d = left;
+                u = h;
+                st.H[r] = h;
+            }
+            st.k = st.k + 1 == m ? 0 : st.k + 1;
+        } else {
+            const uint4 ct = colT[st.j + 31];
+            const unsigned started = st.j >= 1 ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned left = st.H[r];
+                unsigned t;
+                if (CORE == PK_CORE_FLANK1)
+                    t = d + pk_prmt(ct.x, ct.z, st.selA[r]) + st.selB[r];
+                else if (CORE == PK_CORE_FLANK1R)
+                    t = d + pk_prmt(ct.x, ct.z, st.selA[r]) + (st.selB[r] & started);
+                else
+                    t = d + pk_prmt(ct.x, ct.y, st.selA[r]) + pk_prmt(ct.z, ct.w, st.selB[r]);
+                const unsigned h = __vimax3_u16x2(t, u, left);
+                d = left;
+                u = h;
+                st.H[r] = h;
+            }
+        }
+        st.pm = __viaddmax_u16x2(st.pm, ginc, st.H[R - 1]);
+        if (FC) {
+            if (st.j == st.next_cand) {
+#pragma unroll
+                for (int q = 0; q < QN; ++q) {
+                    uint4 v;
+                    v.x = 4 * q + 0 < R ? st.H[(4 * q + 0) % R] : st.pm;
+                    v.y = 4 * q + 1 < R ? st.H[(4 * q + 1) % R] : st.pm;
+                    v.z = 4 * q + 2 < R ? st.H[(4 * q + 2) % R] : st.pm;
+                    v.w = 4 * q + 3 < R ? st.H[(4 * q + 3) % R] : st.pm;
+                    st.dstF[q * 32] = v;
+                }
+                st.dstF += QN * 32;
+                st.next_cand = st.next_cand + m > colsF ? 0x7fffffff : st.next_cand + m;
+            }
+        }
+        if (BC) {
+            if (st.j == colsB) {
+#pragma unroll
+                for (int q = 0; q < QN; ++q) {
+                    uint4 v;
+                    v.x = 4 * q + 0 < R ? st.H[(4 * q + 0) % R] : st.pm;
+                    v.y = 4 * q + 1 < R ? st.H[(4 * q + 1) % R] : st.pm;
+                    v.z = 4 * q + 2 < R ? st.H[(4 * q + 2) % R] : st.pm;
+                    v.w = 4 * q + 3 < R ? st.H[(4 * q + 3) % R] : st.pm;
+                    dstB[q * 32] = v;
+                }
+            }
+        }
+        ++st.j;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(PK_WARPS * 32, R <= 10 ? 5 : 4)
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
                  int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
@@ -92,6 +186,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const int total_warps = gridDim.x * PK_WARPS;
     const int g = consts->gap;
     const int flags = consts->end_flags;
+    const bool one_table_ok = consts->one_table_ok != 0;
     const bool s1_beg = flags & 1, s1_end = flags & 2, s2_beg = flags & 4, s2_end = flags & 8;
     const bool lane0 = lane == 0;
 
@@ -124,30 +219,11 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         // ---- eligibility (warp-uniform): anything odd goes to the general kernel
         bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 64 <= dims.colt_entries &&
                   m * R * 32 <= dims.prof_words && nW <= dims.w_max && (g * (N + ncols + 40) + 2 * N + 1024) < 65535;
-        int codeFB[R];  // forward code | backward code << 8   (setup only)
-        unsigned selF[R], selB[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
-            int cf = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, cb = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
-            if (i >= 1 && i <= n1) {
-                cf = sc.lut[db[i - 1]];
-                cb = sc.lut[db[n1 - i]];
-            }
-            codeFB[r] = cf | (cb << 8);
-            const unsigned kf = cls_of[cf], kb = cls_of[cb];
-            if ((kf | kb) & 0x80) ok = false;
-            selF[r] = (kf & 7) | 0x8880u;
-            selB[r] = ((kb & 7) << 8) | 0x8088u;
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        if (!ok) {
-            if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
-            continue;
-        }
         __syncwarp();  // previous family's readers of colT / prof are done
-
-        // ---- per-column PRMT tables for the flank phase: columns -31 .. Lmax + 31 (zero tables for j <= 0)
+        // ---- per-column PRMT tables for the flank phase: columns -31 .. Lmax + 31 (zero tables for j <= 0).
+        // One-table path: possible when every column symbol of the phase is A/C/G/T (then the score of a
+        // non-ACGT row symbol does not depend on the column and rides along as an addend).
+        bool acgt = true;
         for (int e = lane; e <= Lmax + 62; e += 32) {
             const int j = e - 31;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -161,10 +237,44 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                     sb = sc.lut[db[n1 - j]];
                 else
                     sb = sc.lut[motif[m - 1 - (j - f.n_fr - 1) % m]];
+                acgt = acgt && sf < 4 && sb < 4;
                 const unsigned long long a = t8f[sf], b = t8b[sb];
                 v = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
             }
             colT[e] = v;
+        }
+        const bool one_table = one_table_ok && __all_sync(0xffffffffu, acgt);
+        int codeFB[R];  // forward code | backward code << 8   (setup only)
+        PkState<R> st;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
+            int cf = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, cb = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
+            if (i >= 1 && i <= n1) {
+                cf = sc.lut[db[i - 1]];
+                cb = sc.lut[db[n1 - i]];
+            }
+            codeFB[r] = cf | (cb << 8);
+            unsigned kf = cls_of[cf], kb = cls_of[cb];
+            if ((kf | kb) & 0x80) ok = false;
+            kf &= 7;
+            kb &= 7;
+            if (one_table) {
+                // bytes 0-3 of the pair {forward table, backward table} = forward classes, 4-7 = backward classes;
+                // selector nibble 8 = sign-replicate of byte 0 = 0x00
+                st.selA[r] = (kf < 4 ? kf : 8u) | 0x0080u | ((kb < 4 ? 4u + kb : 8u) << 8) | 0x8000u;
+                const unsigned af = kf < 4 ? 0u : (unsigned)(t8f[0] >> (8 * kf)) & 0xffu;
+                const unsigned ab = kb < 4 ? 0u : (unsigned)(t8b[0] >> (8 * kb)) & 0xffu;
+                st.selB[r] = af | (ab << 16);
+            } else {
+                st.selA[r] = kf | 0x8880u;
+                st.selB[r] = (kb << 8) | 0x8088u;
+            }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) {
+            if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
+            continue;
         }
         // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
         for (int k = 0; k < m; ++k) {
@@ -179,7 +289,6 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
 
         // ---- borders (biased by g * (row + col))
-        unsigned H[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int I = lane * R + r + 1, i = I - off;
@@ -188,9 +297,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 bf = s1_beg ? 0 : -g * i;
                 bb = s1_end ? (i == n1 ? -g : 0) : -g * i;
             }
-            H[r] = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
+            st.H[r] = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
         }
-        unsigned prev_up;
         {
             const int I = lane * R, i = I - off;
             int bf = 0, bb = 0;
@@ -198,136 +306,75 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 bf = s1_beg ? 0 : -g * i;
                 bb = s1_end ? 0 : -g * i;  // i < n1 here
             }
-            prev_up = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
+            st.prev_up = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
         }
-        unsigned topv = 0u;  // top border of the column lane 0 computes next
-        unsigned pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
-        int next_cand = f.n_fl + m * a_lo, w = 0, bslot = nW;
-        int j = 1 - lane;  // column this lane computes in the current step
+        st.topv = 0u;  // top border of the column lane 0 computes next
+        st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
+        st.next_cand = f.n_fl + m * a_lo;
+        st.j = 1 - lane;  // column this lane computes in the current step
+        st.k = 0;
+        st.dstF = scr + lane;
+        uint4 *dstB = scr + (size_t)nW * (QN * 32) + lane;
         __syncwarp();
 
+        // step ranges (warp-uniform).  Lane t is at column c during step c + t - 1.
         const int nsteps = ncols + 31;
-        const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first motif-phase step (warp-uniform)
-        const int first_evt = next_cand < colsB ? next_cand : colsB;  // first captured column; lane 0 is there at
-        const int s_cap = first_evt - 1;                              // step first_evt - 1
+        const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first motif-phase step
+        const int fc_begin = st.next_cand - 1;                       // forward captures: [fc_begin, nsteps)
+        const int bc_begin = colsB - 1, bc_end = colsB + 31;         // backward capture: [bc_begin, bc_end)
 
-#define PK_PROLOGUE()                                                 \
-    unsigned up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);        \
-    topv += tinc;                                                     \
-    up_in = lane0 ? topv : up_in;                                     \
-    unsigned d = prev_up, u = up_in;                                  \
-    prev_up = up_in;
-
-#define PK_CORE_FLANK()                                                                                     \
-    {                                                                                                       \
-        const uint4 ct = colT[j + 31];                                                                      \
-        _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                     \
-            const unsigned left = H[r];                                                                     \
-            const unsigned t = d + pk_prmt(ct.x, ct.y, selF[r]) + pk_prmt(ct.z, ct.w, selB[r]);             \
-            const unsigned h = __vimax3_u16x2(t, u, left);                                                  \
-            d = left;                                                                                       \
-            u = h;                                                                                          \
-            H[r] = h;                                                                                       \
-        }                                                                                                   \
-    }
-
-#define PK_CORE_PROF()                                                                                      \
-    {                                                                                                       \
-        const unsigned *pp = prof + k * (R * 32) + lane;                                                    \
-        _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                     \
-            const unsigned left = H[r];                                                                     \
-            const unsigned t = d + pp[r * 32];                                                              \
-            const unsigned h = __vimax3_u16x2(t, u, left);                                                  \
-            d = left;                                                                                       \
-            u = h;                                                                                          \
-            H[r] = h;                                                                                       \
-        }                                                                                                   \
-        k = k + 1 == m ? 0 : k + 1;                                                                         \
-    }
-
-// capture of candidate columns (forward half) and of the final backward column: predicated 128-bit stores
-#define PK_CAPTURE()                                                                                        \
-    {                                                                                                       \
-        const bool c1 = j == next_cand, c2 = j == colsB;                                                    \
-        if (c1 | c2) {                                                                                      \
-            const int slot = c1 ? w : nW;                                                                   \
-            uint4 *dst = scr + (size_t)slot * (QN * 32) + lane;                                             \
-            _Pragma("unroll") for (int q = 0; q < QN; ++q) {                                                \
-                uint4 v;                                                                                    \
-                v.x = 4 * q + 0 < R ? H[(4 * q + 0) % R] : pm;                                              \
-                v.y = 4 * q + 1 < R ? H[(4 * q + 1) % R] : pm;                                              \
-                v.z = 4 * q + 2 < R ? H[(4 * q + 2) % R] : pm;                                              \
-                v.w = 4 * q + 3 < R ? H[(4 * q + 3) % R] : pm;                                              \
-                dst[q * 32] = v;                                                                            \
-            }                                                                                               \
-            if (c2) bslot = slot;                                                                           \
-            if (c1) {                                                                                       \
-                ++w;                                                                                        \
-                next_cand = w < nW ? next_cand + m : 0x7fffffff;                                            \
-            }                                                                                               \
-        }                                                                                                   \
-    }
-
-#define PK_EPILOGUE()                                  \
-    pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);         \
-    ++j;
+#define PK_RUN(CORE, FC, BC, END) \
+    pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, tinc, ginc, colT, prof, m, colsF, colsB, dstB)
 
         int s = 0;
         // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
-        // maximum of the last row starts from scratch.
-        {
-            const int e1 = s_star < 31 ? s_star : 31;
-            for (; s < e1; ++s) {
-                PK_PROLOGUE()
-                PK_CORE_FLANK()
-                pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);
-                if (s >= s_cap) PK_CAPTURE()
-                ++j;
-            }
-            pm = 0u;
-            if (s_cap >= s_star) {
-                for (; s < s_star; ++s) {
-                    PK_PROLOGUE()
-                    PK_CORE_FLANK()
-                    PK_EPILOGUE()
-                }
+        // maximum of the last row starts from scratch.  Captures this early are rare (very short tracts).
+        for (int part = 0; part < 2; ++part) {
+            const int e = part == 0 ? (s_star < 31 ? s_star : 31) : s_star;
+            const bool any_cap = fc_begin < e || bc_begin < e;
+            if (one_table) {
+                if (part == 0)
+                    PK_RUN(PK_CORE_FLANK1R, true, true, e);
+                else if (any_cap)
+                    PK_RUN(PK_CORE_FLANK1, true, true, e);
+                else
+                    PK_RUN(PK_CORE_FLANK1, false, false, e);
             } else {
-                for (; s < s_star; ++s) {
-                    PK_PROLOGUE()
-                    PK_CORE_FLANK()
-                    pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);
-                    if (s >= s_cap) PK_CAPTURE()
-                    ++j;
+                if (any_cap)
+                    PK_RUN(PK_CORE_FLANK2, true, true, e);
+                else
+                    PK_RUN(PK_CORE_FLANK2, false, false, e);
+            }
+            if (part == 0) st.pm = 0u;
+        }
+        // ---- motif phase (packed profile from shared memory), cut where the capture switches change
+        if (s < nsteps) {
+            st.k = (st.j - Lmax - 1) % m;  // j >= Lmax + 1 on every lane here
+            while (s < nsteps) {
+                const bool fc = s >= fc_begin, bc = s >= bc_begin && s < bc_end;
+                int e = nsteps;
+                if (fc_begin > s && fc_begin < e) e = fc_begin;
+                if (bc_begin > s && bc_begin < e) e = bc_begin;
+                if (bc_end > s && bc_end < e) e = bc_end;
+                if (fc) {
+                    if (bc)
+                        PK_RUN(PK_CORE_PROF, true, true, e);
+                    else
+                        PK_RUN(PK_CORE_PROF, true, false, e);
+                } else {
+                    if (bc)
+                        PK_RUN(PK_CORE_PROF, false, true, e);
+                    else
+                        PK_RUN(PK_CORE_PROF, false, false, e);
                 }
             }
         }
-        // ---- motif phase (packed profile from shared memory)
-        if (s < nsteps) {
-            int k = (j - Lmax - 1) % m;  // j >= Lmax + 1 on every lane here
-            const int e2 = s_cap < nsteps ? (s_cap > s ? s_cap : s) : nsteps;
-            for (; s < e2; ++s) {
-                PK_PROLOGUE()
-                PK_CORE_PROF()
-                PK_EPILOGUE()
-            }
-            for (; s < nsteps; ++s) {
-                PK_PROLOGUE()
-                PK_CORE_PROF()
-                pm = __viaddmax_u16x2(pm, ginc, H[R - 1]);
-                PK_CAPTURE()
-                ++j;
-            }
-        }
-#undef PK_PROLOGUE
-#undef PK_CORE_FLANK
-#undef PK_CORE_PROF
-#undef PK_CAPTURE
-#undef PK_EPILOGUE
+#undef PK_RUN
 
         // ---- combine: score(n) for every candidate of the window
-        bslot = __shfl_sync(0xffffffffu, bslot, 0);
         __syncwarp();
         const unsigned *scw = (const unsigned *)scr;
+        const int bslot = nW;
         unsigned Bv[R];  // backward value paired with each forward row (low half), 0 for pad rows
 #pragma unroll
         for (int r = 0; r < R; ++r) {
