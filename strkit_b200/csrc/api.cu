@@ -1,5 +1,6 @@
 // api.cu -- C ABI (include/strkit_b200.h), context and batch management, launch orchestration.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -908,14 +909,187 @@ extern "C" int strk_ref_boundary_tables(strk_ctx *ctx, const uint8_t *arena, uin
                          n_loci, out_off, STRK_KERNEL_GENERAL, out);
 }
 
+// One DP pass over `fams` (general kernel) and download of the raw table (int scores, or packed argmax keys).
+template <typename T>
+static int dp_tables_to_host(strk_ctx *ctx, bool ref, const std::vector<FamDesc> &fams, const unsigned char *d_arena,
+                             size_t total_elems, std::vector<T> &host_table) {
+    int b_len = 2, rowlen = 2;
+    for (const FamDesc &f : fams) {
+        const int n1 = f.n_fl + f.n_tr + f.n_fr;
+        b_len = std::max(b_len, n1 + 2);
+        if (n1 > 32 * 16) rowlen = std::max(rowlen, std::max(f.n_fl, f.n_fr) + f.m * f.n_hi + 2);
+    }
+    if (ctx->fams.reserve(fams.size()) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "cannot allocate family descriptors");
+    }
+    void *d_table = nullptr;
+    if (ref) {
+        if (ctx->table64.reserve(total_elems) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(STRK_ERR_NOMEM, "cannot allocate the boundary table");
+        }
+        d_table = ctx->table64.p;
+    } else {
+        if (ctx->table.reserve(total_elems) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(STRK_ERR_NOMEM, "cannot allocate the score table");
+        }
+        d_table = ctx->table.p;
+    }
+    CU(cudaMemcpyAsync(ctx->fams.p, fams.data(), fams.size() * sizeof(FamDesc), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_general(ctx, ref, ctx->fams.p, nullptr, (long long)fams.size(), d_arena, d_table, b_len, rowlen,
+                            ctx->stream);
+    if (rc) return rc;
+    host_table.resize(total_elems);
+    CU(cudaMemcpyAsync(host_table.data(), d_table, total_elems * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return STRK_OK;
+}
+
+// get_ref_repeat_count (repeats.py:73-192) for a batch of loci.  Phase 1: boundary tables (two sg_qe sweeps
+// per locus, every candidate size of a window at once) + replay of the dual-score search -> l_offset /
+// r_offset.  Phase 2: the final get_repeat_count on the adjusted flanks (score tables + replay).  The
+// replays are look-ups only (replay.cuh) and run on the host here: one per locus, not per read.
 extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                                const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
                                const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off,
                                const int32_t *motif_len, int vcf_anchor_size, int respect_coords, int32_t *out) {
-    (void)ctx, (void)arena, (void)arena_bytes, (void)seq_off, (void)lens, (void)start_count, (void)ref_size;
-    (void)rc_params, (void)n_loci, (void)motif_off, (void)motif_len, (void)vcf_anchor_size, (void)respect_coords;
-    (void)out;
-    return set_err(STRK_ERR_UNSUPPORTED, "strk_ref_counts: not implemented yet");
+    if (!ctx || !arena || !seq_off || !lens || !start_count || !ref_size || !rc_params || !motif_off || !motif_len || !out)
+        return set_err(STRK_ERR_ARG, "strk_ref_counts: null argument");
+    if (n_loci <= 0 || n_loci > 0x7ffffff0LL) return set_err(STRK_ERR_ARG, "strk_ref_counts: bad locus count");
+    int rc = validate_reads("strk_ref_counts", arena_bytes, seq_off, lens, n_loci);
+    if (rc) return rc;
+    rc = validate_motifs("strk_ref_counts", arena_bytes, motif_off, motif_len, n_loci);
+    if (rc) return rc;
+    for (int64_t l = 0; l < n_loci; ++l) {
+        if (start_count[l] < 0 || start_count[l] > (1 << 22) || rc_params[3 * l] < 0 || rc_params[3 * l + 1] < 0 ||
+            rc_params[3 * l + 2] < 0 || rc_params[3 * l + 1] > 1000 || rc_params[3 * l + 2] > 1000)
+            return set_err(STRK_ERR_ARG, "strk_ref_counts: bad start count / search parameters for locus %lld", (long long)l);
+    }
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
+    TmpDev tmp;
+    unsigned char *d_arena = nullptr;
+    if (tmp.up(&d_arena, arena, (size_t)arena_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "strk_ref_counts: cannot upload the arena");
+    }
+    std::vector<int> l_off((size_t)n_loci, 0), r_off((size_t)n_loci, 0), n_off_scores((size_t)n_loci, 0);
+    SeenSet seen;
+    const int WD_MAX = (STRK_MAX_WINDOW - 1) / 2;
+
+    // ---- phase 1: boundary extension (skipped with respect_coords, repeats.py:99)
+    if (!respect_coords) {
+        std::vector<int64_t> pending((size_t)n_loci);
+        std::vector<int> wd((size_t)n_loci);
+        for (int64_t l = 0; l < n_loci; ++l) {
+            pending[(size_t)l] = l;
+            wd[(size_t)l] = std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
+        }
+        while (!pending.empty()) {
+            std::vector<FamDesc> fams(pending.size());
+            size_t total = 0;
+            for (size_t q = 0; q < pending.size(); ++q) {
+                const int64_t l = pending[q];
+                FamDesc &f = fams[q];
+                f.db_off = seq_off[l];
+                f.motif_off = motif_off[l];
+                f.n_fl = lens[3 * l], f.n_tr = lens[3 * l + 1], f.n_fr = lens[3 * l + 2], f.m = motif_len[l];
+                // size 0 with an empty flank would be an empty candidate; the replay reports it if it gets there
+                const int lo_min = (f.n_fl == 0 || f.n_fr == 0) ? 1 : 0;
+                f.n_lo = std::max(lo_min, start_count[l] - wd[(size_t)l]);
+                f.n_hi = std::max(f.n_lo, start_count[l] + wd[(size_t)l]);
+                f.out_off = total;
+                total += (size_t)(f.n_hi - f.n_lo + 1);
+            }
+            std::vector<long long> keys;
+            rc = dp_tables_to_host<long long>(ctx, true, fams, d_arena, total * 2, keys);
+            if (rc) return rc;
+            std::vector<int64_t> again;
+            for (size_t q = 0; q < pending.size(); ++q) {
+                const int64_t l = pending[q];
+                const FamDesc &f = fams[q];
+                RefClimbResult cr = climb_ref(keys.data() + 2 * f.out_off, f.n_lo, f.n_hi, start_count[l], rc_params[3 * l],
+                                              rc_params[3 * l + 1], rc_params[3 * l + 2], f.n_fl, f.n_fr, ref_size[l],
+                                              vcf_anchor_size, seen);
+                if (cr.status == 1) {
+                    if (wd[(size_t)l] >= WD_MAX)
+                        return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld left the widest window", (long long)l);
+                    wd[(size_t)l] = std::min(WD_MAX, wd[(size_t)l] * 4);
+                    again.push_back(l);
+                    ctx->stats[5] += 1;
+                    continue;
+                }
+                if (cr.status == 2)
+                    return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld scored no size (max_iters = %d)",
+                                   (long long)l, rc_params[3 * l]);
+                l_off[(size_t)l] = cr.l_offset;
+                r_off[(size_t)l] = cr.r_offset;
+                n_off_scores[(size_t)l] = cr.n_offset_scores;
+            }
+            pending.swap(again);
+        }
+    }
+
+    // ---- phase 2: final count on the adjusted flanks (repeats.py:171-188)
+    {
+        std::vector<int64_t> pending((size_t)n_loci);
+        std::vector<int> wd((size_t)n_loci), start2((size_t)n_loci), nfl2((size_t)n_loci), nfr2((size_t)n_loci);
+        for (int64_t l = 0; l < n_loci; ++l) {
+            pending[(size_t)l] = l;
+            wd[(size_t)l] = std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
+            const int mov_l = std::max(0, l_off[(size_t)l]), mov_r = std::max(0, r_off[(size_t)l]);
+            nfl2[(size_t)l] = lens[3 * l] - mov_l;
+            nfr2[(size_t)l] = lens[3 * l + 2] - mov_r;
+            const int m = motif_len[l];
+            // round() of the float quotient: banker's rounding (repeats.py:182)
+            start2[(size_t)l] = (int)nearbyint(((double)start_count[l] * (double)m + (double)(mov_l + mov_r)) / (double)m);
+        }
+        while (!pending.empty()) {
+            std::vector<FamDesc> fams(pending.size());
+            size_t total = 0;
+            for (size_t q = 0; q < pending.size(); ++q) {
+                const int64_t l = pending[q];
+                FamDesc &f = fams[q];
+                const int n1 = lens[3 * l] + lens[3 * l + 1] + lens[3 * l + 2];
+                f.db_off = seq_off[l];
+                f.motif_off = motif_off[l];
+                f.n_fl = nfl2[(size_t)l], f.n_fr = nfr2[(size_t)l], f.n_tr = n1 - f.n_fl - f.n_fr, f.m = motif_len[l];
+                const int lo_min = (f.n_fl + f.n_fr == 0) ? 1 : 0;
+                f.n_lo = std::max(lo_min, start2[(size_t)l] - wd[(size_t)l]);
+                f.n_hi = std::max(f.n_lo, start2[(size_t)l] + wd[(size_t)l]);
+                f.out_off = total;
+                total += (size_t)(f.n_hi - f.n_lo + 1);
+            }
+            std::vector<int> scores;
+            rc = dp_tables_to_host<int>(ctx, false, fams, d_arena, total, scores);
+            if (rc) return rc;
+            std::vector<int64_t> again;
+            for (size_t q = 0; q < pending.size(); ++q) {
+                const int64_t l = pending[q];
+                const FamDesc &f = fams[q];
+                ClimbResult cr = climb_single(scores.data() + f.out_off, f.n_lo, f.n_hi, start2[(size_t)l], rc_params[3 * l],
+                                              rc_params[3 * l + 1], rc_params[3 * l + 2], ctx->tie_flags, seen);
+                if (cr.status == 1) {
+                    if (wd[(size_t)l] >= WD_MAX)
+                        return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld left the widest window", (long long)l);
+                    wd[(size_t)l] = std::min(WD_MAX, wd[(size_t)l] * 4);
+                    again.push_back(l);
+                    ctx->stats[5] += 1;
+                    continue;
+                }
+                if (cr.status == 2)
+                    return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld scored no size (max_iters = %d)",
+                                   (long long)l, rc_params[3 * l]);
+                int32_t *o = out + 8 * l;
+                o[0] = cr.best_n, o[1] = cr.best_score, o[2] = l_off[(size_t)l], o[3] = r_off[(size_t)l];
+                o[4] = n_off_scores[(size_t)l], o[5] = cr.n_explored, o[6] = f.n_fl, o[7] = f.n_fr;
+            }
+            pending.swap(again);
+        }
+    }
+    return STRK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -223,6 +223,13 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         // ---- per-column PRMT tables for the flank phase: columns -31 .. Lmax + 31 (zero tables for j <= 0).
         // One-table path: possible when every column symbol of the phase is A/C/G/T (then the score of a
         // non-ACGT row symbol does not depend on the column and rides along as an addend).
+        // x % m for 0 <= x < 65536 without a division: x - m * ((x * inv) >> 20), inv = ceil(2^20 / m)
+        const unsigned inv_m = (1048576u + (unsigned)m - 1u) / (unsigned)m;
+        auto mod_m = [&](int x) -> int {
+            int q = (int)(((unsigned)x * inv_m) >> 20);
+            int r_ = x - q * m;
+            return r_ < 0 ? r_ + m : r_;
+        };
         bool acgt = true;
         for (int e = lane; e <= Lmax + 62; e += 32) {
             const int j = e - 31;
@@ -232,11 +239,11 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 if (j <= f.n_fl)
                     sf = sc.lut[db[j - 1]];
                 else
-                    sf = sc.lut[motif[(j - f.n_fl - 1) % m]];
+                    sf = sc.lut[motif[mod_m(j - f.n_fl - 1)]];
                 if (j <= f.n_fr)
                     sb = sc.lut[db[n1 - j]];
                 else
-                    sb = sc.lut[motif[m - 1 - (j - f.n_fr - 1) % m]];
+                    sb = sc.lut[motif[m - 1 - mod_m(j - f.n_fr - 1)]];
                 acgt = acgt && sf < 4 && sb < 4;
                 const unsigned long long a = t8f[sf], b = t8b[sb];
                 v = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
@@ -278,8 +285,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
         for (int k = 0; k < m; ++k) {
-            const int sf = sc.lut[motif[(k + Lmax - f.n_fl) % m]];
-            const int sb = sc.lut[motif[m - 1 - (k + Lmax - f.n_fr) % m]];
+            const int sf = sc.lut[motif[mod_m(k + Lmax - f.n_fl)]];
+            const int sb = sc.lut[motif[m - 1 - mod_m(k + Lmax - f.n_fr)]];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int vf = sc.smat[(codeFB[r] & 0xff) * STRK_NSYM_ + sf] + g2;
@@ -329,27 +336,37 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         int s = 0;
         // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
         // maximum of the last row starts from scratch.  Captures this early are rare (very short tracts).
-        for (int part = 0; part < 2; ++part) {
-            const int e = part == 0 ? (s_star < 31 ? s_star : 31) : s_star;
-            const bool any_cap = fc_begin < e || bc_begin < e;
-            if (one_table) {
-                if (part == 0)
-                    PK_RUN(PK_CORE_FLANK1R, true, true, e);
-                else if (any_cap)
-                    PK_RUN(PK_CORE_FLANK1, true, true, e);
-                else
-                    PK_RUN(PK_CORE_FLANK1, false, false, e);
-            } else {
-                if (any_cap)
-                    PK_RUN(PK_CORE_FLANK2, true, true, e);
-                else
-                    PK_RUN(PK_CORE_FLANK2, false, false, e);
+        {
+            // part 0: ramp-up steps 0..30 (captures compiled in; they are rare this early)
+            const int e0 = s_star < 31 ? s_star : 31;
+            if (one_table)
+                PK_RUN(PK_CORE_FLANK1R, true, true, e0);
+            else
+                PK_RUN(PK_CORE_FLANK2, true, true, e0);
+            st.pm = 0u;
+            // part 1: cut where the capture switches change, like the motif phase
+            while (s < s_star) {
+                const bool fc = s >= fc_begin, bc = s >= bc_begin && s < bc_end;
+                int e = s_star;
+                if (fc_begin > s && fc_begin < e) e = fc_begin;
+                if (bc_begin > s && bc_begin < e) e = bc_begin;
+                if (bc_end > s && bc_end < e) e = bc_end;
+                if (one_table) {
+                    if (fc || bc)
+                        PK_RUN(PK_CORE_FLANK1, true, true, e);
+                    else
+                        PK_RUN(PK_CORE_FLANK1, false, false, e);
+                } else {
+                    if (fc || bc)
+                        PK_RUN(PK_CORE_FLANK2, true, true, e);
+                    else
+                        PK_RUN(PK_CORE_FLANK2, false, false, e);
+                }
             }
-            if (part == 0) st.pm = 0u;
         }
         // ---- motif phase (packed profile from shared memory), cut where the capture switches change
         if (s < nsteps) {
-            st.k = (st.j - Lmax - 1) % m;  // j >= Lmax + 1 on every lane here
+            st.k = mod_m(st.j - Lmax - 1);  // j >= Lmax + 1 on every lane here
             while (s < nsteps) {
                 const bool fc = s >= fc_begin, bc = s >= bc_begin && s < bc_end;
                 int e = nsteps;

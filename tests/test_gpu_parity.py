@@ -226,3 +226,45 @@ def test_invalid_inputs_raise(sb):
         sb.Engine(gap_open=7, gap_extend=1)  # affine gaps are not what the reference uses
     with pytest.raises(NotImplementedError):
         sb.get_repeat_count(3, "CAGCAG", "A", "T", "CAG", sb.RepeatCountParams("comp", 50, 3, 1))
+
+
+def test_get_ref_repeat_count_golden(sb, golden):
+    """Drop-in get_ref_repeat_count against vectors produced by the reference's own repeats.py:73-192."""
+    for c in golden["ref"]:
+        e = c["expect"]
+        params = sb.RepeatCountParams("repalign", c["max_iters"], c["local_search_range"], c["step_size"])
+        res = sb.get_ref_repeat_count(c["start_count"], c["tr_seq"], c["flank_left_seq"], c["flank_right_seq"],
+                                      c["motif"], c["ref_size"], c["vcf_anchor_size"], params, c["respect_coords"])
+        (cn, score), lo, ro, (n_off, n_fin), (fl2, tr2, fr2) = res
+        assert (cn, score, lo, ro, n_off, n_fin) == (e["cn"], e["score"], e["l_offset"], e["r_offset"],
+                                                     e["n_offset_scores"], e["n_iters_final"]), c
+        assert (fl2, tr2, fr2) == (e["fl"], e["tr"], e["fr"])
+
+
+def test_ref_counts_batch_with_reference_tiers(sb, oracle):
+    """One C-ABI call for many loci, search parameters tiered like repeat_count_params.py:17-42
+    (steps of 3 / 5 / 15 for large reference tracts)."""
+    rng = np.random.default_rng(21)
+    fams, starts, ref_sizes, rcs = [], [], [], []
+    for i in range(40):
+        m = int(rng.integers(2, 7))
+        motif = "".join(rng.choice(list("ACGT"), size=m))
+        k = int(rng.choice([12, 30, 80, 210, 450])) if i % 4 else int(rng.integers(5, 40))
+        tr = mutate(rng, motif * k, 0.01, 0.005, 0.005)
+        fl = "".join(rng.choice(list("ACGT"), size=70))
+        fr = "".join(rng.choice(list("ACGT"), size=70))
+        if i % 3 == 0:  # repeat spills into the flanks
+            fl = fl[:60] + (motif * 10)[-10:]
+            fr = (motif * 10)[:8] + fr[8:]
+        est = round(len(tr) / m)
+        p = sb.get_reference_rc_params("repalign", est * (10 if i % 5 == 0 else 1), 250)  # exercise every tier
+        fams.append((motif, tr, fl, fr))
+        starts.append(est)
+        ref_sizes.append(len(tr))
+        rcs.append([p.max_iters, p.initial_local_search_range, p.initial_step_size])
+    eng = sb.Engine()
+    got = eng.ref_counts(families_to_batch(fams), starts, ref_sizes, np.array(rcs), vcf_anchor_size=5)
+    for i, (motif, tr, fl, fr) in enumerate(fams):
+        (cn, score), lo, ro, (n_off, n_fin), (fl2, tr2, fr2) = oracle.get_ref_repeat_count(
+            starts[i], tr, fl, fr, motif, ref_sizes[i], 5, rcs[i][0], rcs[i][1], rcs[i][2])
+        assert got[i].tolist() == [cn, score, lo, ro, n_off, n_fin, len(fl2), len(fr2)], (i, fams[i][0], rcs[i])

@@ -93,3 +93,26 @@ def test_synth_generator_is_deterministic_and_sane(oracle):
     out, _ = oracle.count_loci(a.arena, a.seq_off, a.lens, a.est_cn, a.read_begin, a.motif_off, a.motif_len,
                                n_threads=4)
     assert (out[:, 0] == sb.true_cn.numpy()).mean() > 0.97
+
+
+def test_install_rebinds_strkit_names(monkeypatch):
+    """install() must patch both strkit.call.repeats and the from-imported names in strkit.call.call_locus
+    (call_locus.py:32).  Uses stand-in modules: the real strkit is not installable in the test box."""
+    import sys
+    import types
+
+    import strkit_b200
+    from strkit_b200 import repeats as ours
+
+    pkg, call = types.ModuleType("strkit"), types.ModuleType("strkit.call")
+    rep, loc = types.ModuleType("strkit.call.repeats"), types.ModuleType("strkit.call.call_locus")
+    rep.get_repeat_count = rep.get_ref_repeat_count = lambda *a, **k: "reference"
+    loc.get_repeat_count, loc.get_ref_repeat_count = rep.get_repeat_count, rep.get_ref_repeat_count
+    for name, mod in (("strkit", pkg), ("strkit.call", call), ("strkit.call.repeats", rep),
+                      ("strkit.call.call_locus", loc)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    patched = strkit_b200.install()
+    assert len(patched) == 4
+    assert loc.get_repeat_count is ours.get_repeat_count and rep.get_ref_repeat_count is ours.get_ref_repeat_count
+    strkit_b200.uninstall()
+    assert loc.get_repeat_count() == "reference" and rep.get_ref_repeat_count() == "reference"
