@@ -13,8 +13,10 @@ from .engine import KERNEL_AUTO, KERNEL_GENERAL, MODE_SG, MODE_SG_QE, DeviceBatc
 from .install import install, uninstall
 from .repeat_count_params import RepeatCountParams, get_reference_rc_params
 from .repeats import get_ref_repeat_count, get_repeat_count
+from .sharding import count_reads_sharded, partition_catalog
 
 __version__ = "0.1.0"
 __all__ = ["LocusReads", "ReadBatch", "pack_loci", "Engine", "DeviceBatch", "default_engine", "device_count",
            "MODE_SG", "MODE_SG_QE", "KERNEL_AUTO", "KERNEL_GENERAL", "RepeatCountParams", "get_reference_rc_params",
-           "get_repeat_count", "get_ref_repeat_count", "install", "uninstall"]
+           "get_repeat_count", "get_ref_repeat_count", "install", "uninstall", "count_reads_sharded",
+           "partition_catalog"]
