@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -10,6 +11,7 @@
 #include "../../include/strkit_b200.h"
 #include "dp_general.cuh"
 #include "dp_packed.cuh"
+#include "plan.cuh"
 #include "int_peak.cuh"
 #include "replay.cuh"
 #include "strk_common.cuh"
@@ -88,6 +90,8 @@ struct strk_ctx {
     DevBuf<uint4> pk_scratch;        // captured DP columns of the packed kernel (per resident warp)
     unsigned int *d_queue = nullptr;  // [0] work queue, [1] miss counter
     double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
+    PlanStats *d_plan = nullptr;      // device-side planning counters
+    unsigned int *d_bin_off = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     struct strk_batch *reuse = nullptr;  // device buffers recycled by strk_count_reads
@@ -105,10 +109,10 @@ struct strk_batch {
     long long *d_read_begin = nullptr;
     int *d_out = nullptr;
     unsigned char *d_status = nullptr;
-    // host mirrors used for planning (scratch sizing, widening lists)
-    std::vector<int> h_lens, h_est, h_motif_len, h_read_locus, h_order;
+    // host mirror used by the widening passes (per locus, small); per-read planning happens on the device
     std::vector<long long> h_read_begin;
-    int max_n1 = 0;
+    DevBuf<unsigned char> bin;
+    int max_n1 = 0, mb_cols_base = 0, mb_m = 0;
     // work plan over h_order: [0, n_general) general-kernel-only reads, then one segment per packed R
     long long n_general = 0;
     long long bin_off[9] = {0}, bin_cnt[9] = {0};  // index R / 2
@@ -116,6 +120,7 @@ struct strk_batch {
     void release() {
         arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
         motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
+        bin.release();
     }
 };
 
@@ -216,6 +221,8 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     CU(cudaMemcpy(ctx->d_consts, &ctx->h_consts, sizeof(ScoreConsts), cudaMemcpyHostToDevice));
     CU(cudaMalloc((void **)&ctx->d_queue, 4 * sizeof(unsigned int)));
     CU(cudaMalloc((void **)&ctx->d_acc, 4 * sizeof(double)));
+    CU(cudaMalloc((void **)&ctx->d_plan, sizeof(PlanStats)));
+    CU(cudaMalloc((void **)&ctx->d_bin_off, 9 * sizeof(unsigned int)));
     for (int k = 0; k < 3; ++k) CU(cudaEventCreate(&ctx->ev[k]));
     *out = ctx;
     return STRK_OK;
@@ -241,6 +248,8 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     if (ctx->d_consts) cudaFree(ctx->d_consts);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     if (ctx->d_acc) cudaFree(ctx->d_acc);
+    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    if (ctx->d_bin_off) cudaFree(ctx->d_bin_off);
     for (int k = 0; k < 3; ++k)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -400,7 +409,7 @@ extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b) {
     return STRK_OK;
 }
 
-// validate + plan + H2D into (possibly recycled) device buffers
+// H2D into (possibly recycled) device buffers, then validation + work planning on the device (plan.cuh)
 static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                       const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
                       const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci) {
@@ -410,81 +419,13 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
         return set_err(STRK_ERR_ARG, "batch: null array");
     if (read_begin[0] != 0 || read_begin[n_loci] != n_reads)
         return set_err(STRK_ERR_ARG, "batch: read_begin must run from 0 to n_reads");
-    for (int64_t l = 0; l < n_loci; ++l)
-        if (read_begin[l + 1] < read_begin[l]) return set_err(STRK_ERR_ARG, "batch: read_begin not monotone");
-    int rc = validate_reads("batch", arena_bytes, seq_off, lens, n_reads);
-    if (rc) return rc;
-    rc = validate_motifs("batch", arena_bytes, motif_off, motif_len, n_loci);
-    if (rc) return rc;
-    for (int64_t r = 0; r < n_reads; ++r)
-        if (est_cn[r] < 0 || est_cn[r] > (1 << 22))
-            return set_err(STRK_ERR_ARG, "batch: est_cn[%lld] = %d out of range", (long long)r, est_cn[r]);
-
     CU(cudaSetDevice(ctx->device));
     b->n_reads = n_reads;
     b->n_loci = n_loci;
-    b->h_lens.assign(lens, lens + 3 * n_reads);
-    b->h_est.assign(est_cn, est_cn + n_reads);
-    b->h_motif_len.assign(motif_len, motif_len + n_loci);
     b->h_read_begin.assign(read_begin, read_begin + n_loci + 1);
-    b->h_read_locus.resize((size_t)n_reads);
-    for (int64_t l = 0; l < n_loci; ++l)
-        for (int64_t r = read_begin[l]; r < read_begin[l + 1]; ++r) b->h_read_locus[(size_t)r] = (int)l;
-
-    // cost-sorted work order: longest db first (counting sort on n1) ...
-    int max_n1 = 0;
-    for (int64_t r = 0; r < n_reads; ++r) max_n1 = std::max(max_n1, lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]);
-    b->max_n1 = max_n1;
-    std::vector<int> sorted((size_t)n_reads);
-    {
-        std::vector<long long> cnt((size_t)max_n1 + 2, 0);
-        for (int64_t r = 0; r < n_reads; ++r) cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++;
-        long long acc = 0;
-        for (size_t k = 0; k < cnt.size(); ++k) {
-            long long c = cnt[k];
-            cnt[k] = acc;
-            acc += c;
-        }
-        for (int64_t r = 0; r < n_reads; ++r)
-            sorted[(size_t)cnt[(size_t)(max_n1 - (lens[3 * r] + lens[3 * r + 1] + lens[3 * r + 2]))]++] = (int)r;
-    }
-    // ... then segmented: reads only the general kernel can take, followed by one segment per packed R
-    std::vector<int> &order = b->h_order;
-    order.clear();
-    order.reserve((size_t)n_reads);
-    {
-        std::vector<unsigned char> bin((size_t)n_reads);
-        long long cnt[9] = {0};
-        for (int k = 0; k < 9; ++k) b->bin_mmax[k] = b->bin_flank[k] = 0;
-        for (int64_t r = 0; r < n_reads; ++r) {
-            const int fl = lens[3 * r], fr = lens[3 * r + 2], n1 = fl + lens[3 * r + 1] + fr;
-            const int m = motif_len[(size_t)b->h_read_locus[(size_t)r]];
-            int R = ctx->h_consts.packed_ok ? strk_pick_rows_packed(n1 + 1) : 0;
-            if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128) R = 0;
-            bin[(size_t)r] = (unsigned char)(R / 2);
-            cnt[R / 2]++;
-            if (R) {
-                b->bin_mmax[R / 2] = std::max(b->bin_mmax[R / 2], m);
-                b->bin_flank[R / 2] = std::max(b->bin_flank[R / 2], std::max(fl, fr));
-            }
-        }
-        long long acc = 0;
-        b->n_general = cnt[0];
-        long long start[9];
-        start[0] = 0;
-        acc = cnt[0];
-        for (int k = 8; k >= 1; --k) {
-            start[k] = acc;
-            b->bin_off[k] = acc;
-            b->bin_cnt[k] = cnt[k];
-            acc += cnt[k];
-        }
-        order.resize((size_t)n_reads);
-        for (int64_t q = 0; q < n_reads; ++q) {
-            const int r = sorted[(size_t)q];
-            order[(size_t)start[bin[(size_t)r]]++] = r;
-        }
-    }
+    b->n_general = 0;
+    for (int k = 0; k < 9; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
+    b->max_n1 = b->mb_cols_base = b->mb_m = 0;
 
     cudaStream_t st = ctx->stream;
     cudaError_t e = cudaSuccess;
@@ -497,19 +438,76 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     UP(read_begin, d_read_begin, (const long long *)read_begin, n_loci + 1);
     UP(motif_off, d_motif_off, (const unsigned long long *)motif_off, n_loci);
     UP(motif_len, d_motif_len, (const int *)motif_len, n_loci);
-    UP(read_locus, d_read_locus, (const int *)b->h_read_locus.data(), n_reads);
-    UP(order, d_order, (const int *)order.data(), n_reads);
 #undef UP
-    if (e == cudaSuccess) e = b->out.reserve((size_t)(n_reads ? n_reads : 1) * 4);
+    const size_t nr = (size_t)(n_reads ? n_reads : 1);
+    if (e == cudaSuccess) e = b->read_locus.reserve(nr);
+    if (e == cudaSuccess) e = b->order.reserve(nr);
+    if (e == cudaSuccess) e = b->bin.reserve(nr);
+    if (e == cudaSuccess) e = b->out.reserve(nr * 4);
     if (e == cudaSuccess) e = b->status.reserve((size_t)(n_loci ? n_loci : 1));
+    b->d_read_locus = b->read_locus.p;
+    b->d_order = b->order.p;
     b->d_out = b->out.p;
     b->d_status = b->status.p;
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the caller's buffers may go away after return
     if (e != cudaSuccess) {
         cudaGetLastError();
         return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "batch upload: %s",
                        cudaGetErrorString(e));
     }
+    if (n_reads == 0) {
+        CU(cudaStreamSynchronize(st));
+        return STRK_OK;
+    }
+    // ---- plan on the device
+    PlanStats hp;
+    CU(cudaMemsetAsync(ctx->d_plan, 0, sizeof(PlanStats), st));
+    CU(cudaMemsetAsync(&ctx->d_plan->first_error, 0xff, sizeof(unsigned long long), st));
+    const int T = 256;
+    plan_loci_kernel<<<(unsigned)((n_loci + T - 1) / T), T, 0, st>>>(b->d_read_begin, n_loci, n_reads, b->d_motif_off,
+                                                                     b->d_motif_len, arena_bytes, b->d_read_locus,
+                                                                     ctx->d_plan);
+    CU(cudaGetLastError());
+    // the read scan dereferences read_locus / motif_len: stop here if the locus table itself is broken
+    CU(cudaMemcpyAsync(&hp, ctx->d_plan, sizeof(PlanStats), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hp.first_error == ~0ull) {
+        plan_reads_scan_kernel<<<(unsigned)((n_reads + T - 1) / T), T, 0, st>>>(
+            b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_len, n_reads, arena_bytes,
+            ctx->h_consts.packed_ok, b->bin.p, ctx->d_plan);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&hp, ctx->d_plan, sizeof(PlanStats), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (hp.first_error != ~0ull) {
+        const long long idx = (long long)(hp.first_error >> 8);
+        static const char *what[] = {"", "has a negative length", "is empty (fl + tr + fr has no bases)", "is too long",
+                                     "runs past the end of the arena", "has an out-of-range est_cn", "has an empty motif",
+                                     "has a motif that runs past the end of the arena", "has a non-monotone read_begin"};
+        const int kind = (int)(hp.first_error & 0xff);
+        return set_err(STRK_ERR_ARG, "batch: %s %lld %s", kind >= PLAN_ERR_MOTIF_EMPTY ? "locus" : "read", idx,
+                       what[kind <= 8 ? kind : 0]);
+    }
+    // segment offsets: general first, then packed classes from R = 16 down to 2
+    unsigned off[9];
+    unsigned acc = hp.bin_cnt[0];
+    off[0] = 0;
+    b->n_general = hp.bin_cnt[0];
+    for (int k = 8; k >= 1; --k) {
+        off[k] = acc;
+        b->bin_off[k] = acc;
+        b->bin_cnt[k] = hp.bin_cnt[k];
+        b->bin_mmax[k] = hp.bin_mmax[k];
+        b->bin_flank[k] = hp.bin_flank[k];
+        acc += hp.bin_cnt[k];
+    }
+    b->max_n1 = hp.max_n1;
+    b->mb_cols_base = hp.mb_cols_base;
+    b->mb_m = hp.mb_m;
+    CU(cudaMemcpyAsync(ctx->d_bin_off, off, sizeof(off), cudaMemcpyHostToDevice, st));
+    plan_reads_scatter_kernel<<<(unsigned)((n_reads + T - 1) / T), T, 0, st>>>(b->bin.p, n_reads, ctx->d_bin_off,
+                                                                              ctx->d_plan, b->d_order);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));  // `off` is on this stack frame; the caller's buffers may go away after return
     return STRK_OK;
 }
 
@@ -531,22 +529,11 @@ extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t a
     return STRK_OK;
 }
 
-// longest boundary row any multi-pass family of the slot list needs (+1), and the longest db (+1)
-static void scratch_dims(const strk_batch *b, const int *read_ids, long long n_slots, int wd, int *b_len,
-                         int *rowlen) {
-    int mx_n1 = 0, mx_cols = 0;
-    for (long long s = 0; s < n_slots; ++s) {
-        const long long r = read_ids ? read_ids[s] : s;
-        const int fl = b->h_lens[3 * r], tr = b->h_lens[3 * r + 1], fr = b->h_lens[3 * r + 2];
-        const int n1 = fl + tr + fr;
-        mx_n1 = std::max(mx_n1, n1);
-        if (n1 > 32 * 16) {
-            const int m = b->h_motif_len[(size_t)b->h_read_locus[(size_t)r]];
-            mx_cols = std::max(mx_cols, std::max(fl, fr) + m * (b->h_est[(size_t)r] + wd));
-        }
-    }
-    *b_len = mx_n1 + 2;
-    *rowlen = mx_cols + 2;
+// scratch sizes of the general kernel: backward column (longest db + 2) and, for multi-pass reads (db > 512),
+// the boundary row (longest candidate prefix + 2)
+static void scratch_dims(const strk_batch *b, int wd, int *b_len, int *rowlen) {
+    *b_len = b->max_n1 + 2;
+    *rowlen = b->max_n1 > 32 * 16 ? b->mb_cols_base + b->mb_m * wd + 2 : 2;
 }
 
 extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int local_search_range, int step_size,
@@ -562,8 +549,14 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
     }
     CU(cudaMemsetAsync(ctx->d_acc, 0, 4 * sizeof(double), st));
 
-    int wd = local_search_range + step_size + 4;
-    if (wd < 8) wd = 8;
+    // first-pass window half-width around the per-read estimate: the replay of a well-started search visits
+    // start +- (range + step); the margin absorbs the carried start offset.  STRK_WD overrides (tuning only).
+    int wd = local_search_range + step_size + 2;
+    if (wd < 6) wd = 6;
+    if (const char *env = getenv("STRK_WD")) {
+        int v = atoi(env);
+        if (v >= 1 && v <= 64) wd = v;
+    }
     long long n_slots = b->n_reads;
     long long n_list = b->n_loci;
     const int *d_read_ids = nullptr, *d_locus_ids = nullptr;
@@ -581,7 +574,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             return set_err(STRK_ERR_NOMEM, "cannot allocate score tables for %lld reads x %d sizes", n_slots, W);
         }
         int b_len, rowlen;
-        scratch_dims(b, pass ? h_read_ids.data() : nullptr, n_slots, wd, &b_len, &rowlen);
+        scratch_dims(b, wd, &b_len, &rowlen);
         const int threads = 256;
         plan_reads_kernel<<<(unsigned)((n_slots + threads - 1) / threads), threads, 0, st>>>(
             d_read_ids, n_slots, b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_off, b->d_motif_len, wd,
