@@ -602,7 +602,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                 PackedDims dims;
                 dims.colt_entries = b->bin_flank[k] + 64;
                 dims.prof_words = b->bin_mmax[k] * R * 32;
-                dims.w_max = W;
+                dims.w_max = (W + 3) / 4 * 4;
                 if (pk_smem_bytes(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
                     rc = launch_general(ctx, false, ctx->fams.p, b->d_order + b->bin_off[k], b->bin_cnt[k], b->d_arena,
@@ -836,7 +836,7 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
             PackedDims dims;
             dims.colt_entries = flank[k] + 64;
             dims.prof_words = mmax[k] * 2 * k * 32;
-            dims.w_max = wmax[k];
+            dims.w_max = (wmax[k] + 3) / 4 * 4;
             if (pk_smem_bytes(2 * k, dims) > 200 * 1024) {
                 rc = launch_general(ctx, false, d_fams, d_lists + offs[k], (long long)lists[k].size(), d_arena, d_table,
                                     b_len, rowlen, ctx->stream);

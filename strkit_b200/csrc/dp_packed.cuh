@@ -51,9 +51,13 @@ __host__ __device__ inline int pk_quads(int R) { return (R + 1 + 3) / 4; }  // H
 __host__ __device__ inline size_t pk_scratch_words_per_warp(int R, int w_max) {
     return (size_t)(w_max + 1) * pk_quads(R) * 32 * 4;
 }
+// per-warp shared memory: [colT uint4 x colt_entries][prof u32 x prof_words][encoded db + motif bytes]
+__host__ __device__ inline size_t pk_code_bytes(int R) { return (size_t)(32 * R + 128 + 15) / 16 * 16; }
+__host__ __device__ inline size_t pk_smem16_per_warp(int R, const PackedDims &d) {
+    return (size_t)d.colt_entries + ((size_t)d.prof_words * 4 + 15) / 16 + pk_code_bytes(R) / 16;
+}
 __host__ __device__ inline size_t pk_smem_bytes(int R, const PackedDims &d) {
-    (void)R;
-    return ((size_t)d.colt_entries * 16 + (size_t)d.prof_words * 4 + 15) / 16 * 16 * PK_WARPS;
+    return pk_smem16_per_warp(R, d) * 16 * PK_WARPS;
 }
 
 // Raw PRMT (generic mode).  NOT __byte_perm: that intrinsic masks the selector with 0x7777, which costs an
@@ -72,21 +76,23 @@ struct PkState {
     unsigned selA[R];  // PRMT selector (two-table path: forward half; one-table path: both halves)
     unsigned selB[R];  // two-table path: PRMT selector of the backward half; one-table path: packed addend
     unsigned prev_up, topv, pm;
-    int j, k, next_cand;
-    uint4 *dstF;  // next forward capture slot (lane-offset applied)
+    int poff;       // word offset of the current profile column (motif phase)
+    int cand_step;  // step at which this lane reaches the next forward candidate column
+    uint4 *dstF;    // next forward capture slot (lane-offset applied)
 };
 
 // FLANK1R = one-table path during the ramp-up steps: lanes that have not reached column 1 yet must see a
 // zero score, so their addend is masked off
 enum { PK_CORE_FLANK2 = 0, PK_CORE_FLANK1 = 1, PK_CORE_PROF = 2, PK_CORE_FLANK1R = 3 };
 
-// Steps [s, s_end) of the wavefront.  CORE selects the score source, FC / BC switch the predicated captures of
-// forward candidate columns / of the final backward column on.
+// Steps [s, s_end) of the wavefront; lane t computes column s - t + 1 in step s.  CORE selects the score
+// source, FC / BC switch the predicated captures of forward candidate columns / the final backward column on.
 template <int R, int CORE, bool FC, bool BC>
 __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, const bool lane0, const int lane,
-                                       const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ colT,
-                                       const unsigned *__restrict__ prof, const int m, const int colsF,
-                                       const int colsB, uint4 *__restrict__ dstB) {
+                                       const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ ctp,
+                                       const unsigned *__restrict__ prof_lane, const int pstride, const int pwrap,
+                                       const int m, const int last_cand_step, const int bstep,
+                                       uint4 *__restrict__ dstB) {
     constexpr int QN = (R + 1 + 3) / 4;
 #pragma unroll 1
     for (; s < s_end; ++s) {
@@ -96,7 +102,7 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
         unsigned d = st.prev_up, u = up_in;
         st.prev_up = up_in;
         if (CORE == PK_CORE_PROF) {
-            const unsigned *pp = prof + st.k * (R * 32) + lane;
+            const unsigned *pp = prof_lane + st.poff;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned left = st.H[r];
@@ -105,10 +111,10 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
                 u = h;
                 st.H[r] = h;
             }
-            st.k = st.k + 1 == m ? 0 : st.k + 1;
+            st.poff = st.poff + pstride == pwrap ? 0 : st.poff + pstride;
         } else {
-            const uint4 ct = colT[st.j + 31];
-            const unsigned started = st.j >= 1 ? 0xffffffffu : 0u;
+            const uint4 ct = ctp[s];  // = colT[column + 31]
+            const unsigned started = s >= lane ? 0xffffffffu : 0u;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned left = st.H[r];
@@ -127,7 +133,7 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
         }
         st.pm = __viaddmax_u16x2(st.pm, ginc, st.H[R - 1]);
         if (FC) {
-            if (st.j == st.next_cand) {
+            if (s == st.cand_step) {
 #pragma unroll
                 for (int q = 0; q < QN; ++q) {
                     uint4 v;
@@ -138,11 +144,11 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
                     st.dstF[q * 32] = v;
                 }
                 st.dstF += QN * 32;
-                st.next_cand = st.next_cand + m > colsF ? 0x7fffffff : st.next_cand + m;
+                st.cand_step = st.cand_step + m > last_cand_step ? 0x7fffffff : st.cand_step + m;
             }
         }
         if (BC) {
-            if (st.j == colsB) {
+            if (s == bstep) {
 #pragma unroll
                 for (int q = 0; q < QN; ++q) {
                     uint4 v;
@@ -154,7 +160,6 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
                 }
             }
         }
-        ++st.j;
     }
 }
 
@@ -190,13 +195,15 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const bool s1_beg = flags & 1, s1_end = flags & 2, s2_beg = flags & 4, s2_end = flags & 8;
     const bool lane0 = lane == 0;
 
-    const size_t smem16 = ((size_t)dims.colt_entries * 16 + (size_t)dims.prof_words * 4 + 15) / 16;
-    uint4 *colT = smem_raw + (size_t)warp * smem16;  // entry [j + 31] for columns j = -31 .. Lmax + 31
+    uint4 *colT = smem_raw + (size_t)warp * pk_smem16_per_warp(R, dims);  // entry [j + 31], columns -31 .. Lmax + 31
     unsigned *prof = (unsigned *)(colT + dims.colt_entries);
+    unsigned char *codes = (unsigned char *)(prof + (dims.prof_words + 3) / 4 * 4);  // encoded db, then motif
+    unsigned char *mcodes = codes + 32 * R;
     uint4 *scr = scratch + (size_t)warp_global * (size_t)(dims.w_max + 1) * QN * 32;
     const unsigned tinc = (s2_beg ? (unsigned)g : 0u) | ((s2_end ? (unsigned)g : 0u) << 16);
     const unsigned ginc = (unsigned)g | ((unsigned)g << 16);
     const int g2 = 2 * g;
+    const int padF = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, padB = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
 
     for (int fam_idx = warp_global; fam_idx < n_list; fam_idx += total_warps) {
         const int fam_id = list[fam_idx];
@@ -218,32 +225,40 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
         // ---- eligibility (warp-uniform): anything odd goes to the general kernel
         bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 64 <= dims.colt_entries &&
-                  m * R * 32 <= dims.prof_words && nW <= dims.w_max && (g * (N + ncols + 40) + 2 * N + 1024) < 65535;
-        __syncwarp();  // previous family's readers of colT / prof are done
+                  m * R * 32 <= dims.prof_words && m <= 128 && nW <= dims.w_max &&
+                  (g * (N + ncols + 40) + 2 * N + 1024) < 65535;
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) {
+            if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
+            continue;
+        }
+        __syncwarp();  // the previous read's shared-memory readers are done
+
+        // ---- stage the encoded read and motif in shared memory (one coalesced pass over the arena bytes)
+        bool motif_acgt = true;
+        for (int i = lane; i < n1; i += 32) codes[i] = sc.lut[db[i]];
+        for (int k = lane; k < m; k += 32) {
+            const unsigned char c = sc.lut[motif[k]];
+            mcodes[k] = c;
+            motif_acgt = motif_acgt && c < 4;
+        }
+        motif_acgt = __all_sync(0xffffffffu, motif_acgt);
+        __syncwarp();
+
+        // x % m for 0 <= x < 4096 without a division: x - m * ((x * inv) >> 20), inv = ceil(2^20 / m)
+        const unsigned inv_m = (1048576u + (unsigned)m - 1u) / (unsigned)m;
+        auto mod_m = [&](int x) -> int { return x - (int)(((unsigned)x * inv_m) >> 20) * m; };
+
         // ---- per-column PRMT tables for the flank phase: columns -31 .. Lmax + 31 (zero tables for j <= 0).
         // One-table path: possible when every column symbol of the phase is A/C/G/T (then the score of a
         // non-ACGT row symbol does not depend on the column and rides along as an addend).
-        // x % m for 0 <= x < 65536 without a division: x - m * ((x * inv) >> 20), inv = ceil(2^20 / m)
-        const unsigned inv_m = (1048576u + (unsigned)m - 1u) / (unsigned)m;
-        auto mod_m = [&](int x) -> int {
-            int q = (int)(((unsigned)x * inv_m) >> 20);
-            int r_ = x - q * m;
-            return r_ < 0 ? r_ + m : r_;
-        };
         bool acgt = true;
         for (int e = lane; e <= Lmax + 62; e += 32) {
             const int j = e - 31;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (j >= 1) {
-                int sf, sb;
-                if (j <= f.n_fl)
-                    sf = sc.lut[db[j - 1]];
-                else
-                    sf = sc.lut[motif[mod_m(j - f.n_fl - 1)]];
-                if (j <= f.n_fr)
-                    sb = sc.lut[db[n1 - j]];
-                else
-                    sb = sc.lut[motif[m - 1 - mod_m(j - f.n_fr - 1)]];
+                const int sf = j <= f.n_fl ? codes[j - 1] : mcodes[mod_m(j - f.n_fl - 1)];
+                const int sb = j <= f.n_fr ? codes[n1 - j] : mcodes[m - 1 - mod_m(j - f.n_fr - 1)];
                 acgt = acgt && sf < 4 && sb < 4;
                 const unsigned long long a = t8f[sf], b = t8b[sb];
                 v = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
@@ -251,47 +266,60 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             colT[e] = v;
         }
         const bool one_table = one_table_ok && __all_sync(0xffffffffu, acgt);
-        int codeFB[R];  // forward code | backward code << 8   (setup only)
+
+        // ---- row symbols -> PRMT selectors (one-table format first: the profile build uses it too)
         PkState<R> st;
+        unsigned cls[R];  // forward class | backward class << 4 | forward code << 8 | backward code << 16
+        bool rows_ok = true;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
-            int cf = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, cb = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
-            if (i >= 1 && i <= n1) {
-                cf = sc.lut[db[i - 1]];
-                cb = sc.lut[db[n1 - i]];
+            int cf = padF, cb = padB;
+            if (i >= 1) {
+                cf = codes[i - 1];
+                cb = codes[n1 - i];
             }
-            codeFB[r] = cf | (cb << 8);
             unsigned kf = cls_of[cf], kb = cls_of[cb];
-            if ((kf | kb) & 0x80) ok = false;
+            if ((kf | kb) & 0x80) rows_ok = false;
             kf &= 7;
             kb &= 7;
-            if (one_table) {
-                // bytes 0-3 of the pair {forward table, backward table} = forward classes, 4-7 = backward classes;
-                // selector nibble 8 = sign-replicate of byte 0 = 0x00
-                st.selA[r] = (kf < 4 ? kf : 8u) | 0x0080u | ((kb < 4 ? 4u + kb : 8u) << 8) | 0x8000u;
-                const unsigned af = kf < 4 ? 0u : (unsigned)(t8f[0] >> (8 * kf)) & 0xffu;
-                const unsigned ab = kb < 4 ? 0u : (unsigned)(t8b[0] >> (8 * kb)) & 0xffu;
-                st.selB[r] = af | (ab << 16);
-            } else {
-                st.selA[r] = kf | 0x8880u;
-                st.selB[r] = (kb << 8) | 0x8088u;
-            }
+            cls[r] = kf | (kb << 4) | ((unsigned)cf << 8) | ((unsigned)cb << 16);
+            // bytes 0-3 of the pair {forward table, backward table} = forward classes, 4-7 = backward classes;
+            // selector nibble 8 = sign-replicate of byte 0 = 0x00
+            st.selA[r] = (kf < 4 ? kf : 8u) | 0x0080u | ((kb < 4 ? 4u + kb : 8u) << 8) | 0x8000u;
+            const unsigned af = kf < 4 ? 0u : (unsigned)(t8f[0] >> (8 * kf)) & 0xffu;
+            const unsigned ab = kb < 4 ? 0u : (unsigned)(t8b[0] >> (8 * kb)) & 0xffu;
+            st.selB[r] = af | (ab << 16);
         }
-        ok = __all_sync(0xffffffffu, ok);
-        if (!ok) {
+        if (!__all_sync(0xffffffffu, rows_ok)) {  // IUPAC code inside the read
             if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
             continue;
         }
         // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
-        for (int k = 0; k < m; ++k) {
-            const int sf = sc.lut[motif[mod_m(k + Lmax - f.n_fl)]];
-            const int sb = sc.lut[motif[m - 1 - mod_m(k + Lmax - f.n_fr)]];
+        if (one_table_ok && motif_acgt) {
+            for (int k = 0; k < m; ++k) {
+                const unsigned tf = (unsigned)t8f[mcodes[mod_m(k + Lmax - f.n_fl)]];
+                const unsigned tb = (unsigned)t8b[mcodes[m - 1 - mod_m(k + Lmax - f.n_fr)]];
+#pragma unroll
+                for (int r = 0; r < R; ++r) prof[(k * R + r) * 32 + lane] = pk_prmt(tf, tb, st.selA[r]) + st.selB[r];
+            }
+        } else {
+            for (int k = 0; k < m; ++k) {
+                const int sf = mcodes[mod_m(k + Lmax - f.n_fl)];
+                const int sb = mcodes[m - 1 - mod_m(k + Lmax - f.n_fr)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int vf = sc.smat[((cls[r] >> 8) & 0xff) * STRK_NSYM_ + sf] + g2;
+                    const int vb = sc.smat[((cls[r] >> 16) & 0xff) * STRK_NSYM_ + sb] + g2;
+                    prof[(k * R + r) * 32 + lane] = (unsigned)vf | ((unsigned)vb << 16);
+                }
+            }
+        }
+        if (!one_table) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int vf = sc.smat[(codeFB[r] & 0xff) * STRK_NSYM_ + sf] + g2;
-                const int vb = sc.smat[(codeFB[r] >> 8) * STRK_NSYM_ + sb] + g2;
-                prof[(k * R + r) * 32 + lane] = (unsigned)vf | ((unsigned)vb << 16);
+                st.selA[r] = (cls[r] & 7u) | 0x8880u;
+                st.selB[r] = (((cls[r] >> 4) & 7u) << 8) | 0x8088u;
             }
         }
 
@@ -317,25 +345,31 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         st.topv = 0u;  // top border of the column lane 0 computes next
         st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
-        st.next_cand = f.n_fl + m * a_lo;
-        st.j = 1 - lane;  // column this lane computes in the current step
-        st.k = 0;
+        st.poff = 0;
         st.dstF = scr + lane;
         uint4 *dstB = scr + (size_t)nW * (QN * 32) + lane;
-        __syncwarp();
 
         // step ranges (warp-uniform).  Lane t is at column c during step c + t - 1.
+        const int first_cand = f.n_fl + m * a_lo;
         const int nsteps = ncols + 31;
         const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first motif-phase step
-        const int fc_begin = st.next_cand - 1;                       // forward captures: [fc_begin, nsteps)
+        const int fc_begin = first_cand - 1;                         // forward captures: [fc_begin, nsteps)
         const int bc_begin = colsB - 1, bc_end = colsB + 31;         // backward capture: [bc_begin, bc_end)
+        st.cand_step = first_cand + lane - 1;
+        const int last_cand_step = colsF + lane - 1;
+        const int bstep = colsB + lane - 1;
+        const uint4 *ctp = colT + 32 - lane;  // ctp[s] = table of the column this lane computes in step s
+        const unsigned *prof_lane = prof + lane;
+        const int pstride = R * 32, pwrap = m * R * 32;
+        __syncwarp();
 
-#define PK_RUN(CORE, FC, BC, END) \
-    pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, tinc, ginc, colT, prof, m, colsF, colsB, dstB)
+#define PK_RUN(CORE, FC, BC, END)                                                                          \
+    pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,        \
+                            last_cand_step, bstep, dstB)
 
         int s = 0;
         // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
-        // maximum of the last row starts from scratch.  Captures this early are rare (very short tracts).
+        // maximum of the last row starts from scratch.
         {
             // part 0: ramp-up steps 0..30 (captures compiled in; they are rare this early)
             const int e0 = s_star < 31 ? s_star : 31;
@@ -366,7 +400,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         // ---- motif phase (packed profile from shared memory), cut where the capture switches change
         if (s < nsteps) {
-            st.k = mod_m(st.j - Lmax - 1);  // j >= Lmax + 1 on every lane here
+            st.poff = mod_m(s - lane - Lmax) * pstride;  // column s - lane + 1 >= Lmax + 1 on every lane here
             while (s < nsteps) {
                 const bool fc = s >= fc_begin, bc = s >= bc_begin && s < bc_end;
                 int e = nsteps;
@@ -406,29 +440,41 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         const int bextra = (int)(scw[(((size_t)bslot * QN + (R >> 2)) * 32 + 31) * 4 + (R & 3)] >> 16);
         int *out = table + f.out_off;
-        for (int ww = 0; ww < nW; ++ww) {
-            unsigned acc = 0u;
+        constexpr int WB = 4;  // candidates per batch of loads (hides the L2 round trip)
+        for (int w0 = 0; w0 < nW; w0 += WB) {
+            uint4 q4[WB][QN];
 #pragma unroll
-            for (int q = 0; q < QN; ++q) {
-                const uint4 v = scr[((size_t)ww * QN + q) * 32 + lane];
-                if (4 * q + 0 < R) acc = __viaddmax_u16x2(v.x, Bv[(4 * q + 0) % R], acc);
-                if (4 * q + 1 < R) acc = __viaddmax_u16x2(v.y, Bv[(4 * q + 1) % R], acc);
-                if (4 * q + 2 < R) acc = __viaddmax_u16x2(v.z, Bv[(4 * q + 2) % R], acc);
-                if (4 * q + 3 < R) acc = __viaddmax_u16x2(v.w, Bv[(4 * q + 3) % R], acc);
+            for (int b = 0; b < WB; ++b) {
+                const int ww = w0 + b < nW ? w0 + b : nW - 1;
+#pragma unroll
+                for (int q = 0; q < QN; ++q) q4[b][q] = scr[((size_t)ww * QN + q) * 32 + lane];
             }
-            unsigned v = __reduce_max_sync(0xffffffffu, acc & 0xffffu);
-            if (lane0) {
-                const int p = f.n_fl + m * (a_lo + ww);
-                int best = (int)v - g * (N + off + p + colsB);
-                if (s2_end) {
-                    const int flast = (int)(scw[(((size_t)ww * QN + (R >> 2)) * 32 + 31) * 4 + (R & 3)] & 0xffffu);
-                    best = max(best, flast - g * (N + p));
+#pragma unroll
+            for (int b = 0; b < WB; ++b) {
+                const int ww = w0 + b;
+                unsigned acc = 0u;
+#pragma unroll
+                for (int q = 0; q < QN; ++q) {
+                    const uint4 v = q4[b][q];
+                    if (4 * q + 0 < R) acc = __viaddmax_u16x2(v.x, Bv[(4 * q + 0) % R], acc);
+                    if (4 * q + 1 < R) acc = __viaddmax_u16x2(v.y, Bv[(4 * q + 1) % R], acc);
+                    if (4 * q + 2 < R) acc = __viaddmax_u16x2(v.z, Bv[(4 * q + 2) % R], acc);
+                    if (4 * q + 3 < R) acc = __viaddmax_u16x2(v.w, Bv[(4 * q + 3) % R], acc);
                 }
-                if (s2_beg) {
-                    const int border = s1_end ? -g : -g * n1;  // backward cell (n1, 0)
-                    best = max(best, max(bextra - g * (N + colsB), border));
+                const unsigned v = __reduce_max_sync(0xffffffffu, acc & 0xffffu);
+                // lane 31's prefix-max word of this candidate column (forward half)
+                const unsigned pmw = (&q4[b][R >> 2].x)[R & 3];
+                const unsigned flast = __shfl_sync(0xffffffffu, pmw, 31) & 0xffffu;
+                if (lane0 && ww < nW) {
+                    const int p = f.n_fl + m * (a_lo + ww);
+                    int best = (int)v - g * (N + off + p + colsB);
+                    if (s2_end) best = max(best, (int)flast - g * (N + p));
+                    if (s2_beg) {
+                        const int border = s1_end ? -g : -g * n1;  // backward cell (n1, 0)
+                        best = max(best, max(bextra - g * (N + colsB), border));
+                    }
+                    out[ww] = best;
                 }
-                out[ww] = best;
             }
         }
         __syncwarp();
