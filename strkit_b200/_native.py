@@ -10,7 +10,9 @@ import os
 
 __all__ = ["lib", "StrkError", "check", "LIB_PATH", "build_hint"]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstrkit_b200.so")
+# STRKIT_B200_LIB: kernel-variant experiments only (an alternative build of the same C ABI)
+LIB_PATH = os.environ.get("STRKIT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                             "libstrkit_b200.so")
 build_hint = "build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)"
 
 

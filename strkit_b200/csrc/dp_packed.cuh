@@ -68,6 +68,15 @@ __device__ __forceinline__ unsigned pk_prmt(unsigned a, unsigned b, unsigned sel
     return r;
 }
 
+// a + b on the FMA pipe: IMAD with a multiplier the compiler cannot see through (`one` is loaded from the
+// constants block).  The ALU pipe (PRMT, VIMNMX3; 0.5 warp-instructions per clock per scheduler) is what bounds
+// the step loops, so every add that can move to the other pipe is taken off it.
+__device__ __forceinline__ unsigned pk_add(unsigned a, unsigned b, unsigned one) {
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+
 // Per-lane state of one read in flight.  Everything is indexed with compile-time constants after unrolling,
 // so the arrays live in registers.
 template <int R>
@@ -89,7 +98,7 @@ enum { PK_CORE_FLANK2 = 0, PK_CORE_FLANK1 = 1, PK_CORE_PROF = 2, PK_CORE_FLANK1R
 // source, FC / BC switch the predicated captures of forward candidate columns / the final backward column on.
 template <int R, int CORE, bool FC, bool BC>
 __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, const bool lane0, const int lane,
-                                       const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ ctp,
+                                       const unsigned one, const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ ctp,
                                        const unsigned *__restrict__ prof_lane, const int pstride, const int pwrap,
                                        const int m, const int last_cand_step, const int bstep,
                                        uint4 *__restrict__ dstB) {
@@ -114,17 +123,17 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
             st.poff = st.poff + pstride == pwrap ? 0 : st.poff + pstride;
         } else {
             const uint4 ct = ctp[s];  // = colT[column + 31]
-            const unsigned started = s >= lane ? 0xffffffffu : 0u;
+            const unsigned started = s >= lane ? one : 0u;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned left = st.H[r];
                 unsigned t;
                 if (CORE == PK_CORE_FLANK1)
-                    t = d + pk_prmt(ct.x, ct.z, st.selA[r]) + st.selB[r];
-                else if (CORE == PK_CORE_FLANK1R)
-                    t = d + pk_prmt(ct.x, ct.z, st.selA[r]) + (st.selB[r] & started);
+                    t = pk_add(pk_add(d, pk_prmt(ct.x, ct.z, st.selA[r]), one), st.selB[r], one);
+                else if (CORE == PK_CORE_FLANK1R)  // addend * (0 | 1): masked on the FMA pipe as well
+                    t = pk_add(st.selB[r], pk_add(d, pk_prmt(ct.x, ct.z, st.selA[r]), one), started);
                 else
-                    t = d + pk_prmt(ct.x, ct.y, st.selA[r]) + pk_prmt(ct.z, ct.w, st.selB[r]);
+                    t = pk_add(pk_add(d, pk_prmt(ct.x, ct.y, st.selA[r]), one), pk_prmt(ct.z, ct.w, st.selB[r]), one);
                 const unsigned h = __vimax3_u16x2(t, u, left);
                 d = left;
                 u = h;
@@ -192,6 +201,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const int g = consts->gap;
     const int flags = consts->end_flags;
     const bool one_table_ok = consts->one_table_ok != 0;
+    const unsigned one = consts->one;
     const bool s1_beg = flags & 1, s1_end = flags & 2, s2_beg = flags & 4, s2_end = flags & 8;
     const bool lane0 = lane == 0;
 
@@ -265,12 +275,12 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             }
             colT[e] = v;
         }
-        const bool one_table = one_table_ok && __all_sync(0xffffffffu, acgt);
+        const bool cols_acgt = __all_sync(0xffffffffu, acgt);
 
         // ---- row symbols -> PRMT selectors (one-table format first: the profile build uses it too)
         PkState<R> st;
         unsigned cls[R];  // forward class | backward class << 4 | forward code << 8 | backward code << 16
-        bool rows_ok = true;
+        bool rows_ok = true, rows_plain = true;  // plain = A/C/G/T or pad: nothing column-dependent rides in selB
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
@@ -283,6 +293,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             if ((kf | kb) & 0x80) rows_ok = false;
             kf &= 7;
             kb &= 7;
+            rows_plain = rows_plain && (kf < 4 || kf == 7) && (kb < 4 || kb == 7);
             cls[r] = kf | (kb << 4) | ((unsigned)cf << 8) | ((unsigned)cb << 16);
             // bytes 0-3 of the pair {forward table, backward table} = forward classes, 4-7 = backward classes;
             // selector nibble 8 = sign-replicate of byte 0 = 0x00
@@ -295,6 +306,10 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
             continue;
         }
+        // one table per step is enough when the column-independent addend is exact: either every flank-phase
+        // column is A/C/G/T (a non-ACGT row then scores the same in every column), or no row needs an addend
+        // that depends on the column (only the pad rows have one, and theirs never does)
+        const bool one_table = (one_table_ok && cols_acgt) || __all_sync(0xffffffffu, rows_plain);
         // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
         if (one_table_ok && motif_acgt) {
             for (int k = 0; k < m; ++k) {
@@ -364,7 +379,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         __syncwarp();
 
 #define PK_RUN(CORE, FC, BC, END)                                                                          \
-    pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,        \
+    pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, one, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,        \
                             last_cand_step, bstep, dstB)
 
         int s = 0;

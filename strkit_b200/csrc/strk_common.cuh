@@ -31,6 +31,7 @@ struct ScoreConsts {
     unsigned char cls_of[STRK_SMAT_ROWS + 1];  // symbol code -> PRMT row class, 0x80 = not representable
     int packed_ok;                             // every biased score fits a positive byte
     int one_table_ok;                          // N / X / other rows score the same against A, C, G and T
+    unsigned one;                              // = 1, opaque to the compiler: multiplier of the IMAD-pipe adds
 };
 
 // rows per lane of the packed kernel (even values only, 32*R >= n1); 0 = too long for it
