@@ -115,8 +115,8 @@ struct strk_batch {
     int max_n1 = 0, mb_cols_base = 0, mb_m = 0;
     // work plan over h_order: [0, n_general) general-kernel-only reads, then one segment per packed R
     long long n_general = 0;
-    long long bin_off[9] = {0}, bin_cnt[9] = {0};  // index R / 2
-    int bin_mmax[9] = {0}, bin_flank[9] = {0};
+    long long bin_off[STRK_PK_NBIN] = {0}, bin_cnt[STRK_PK_NBIN] = {0};  // index R (0 = general kernel)
+    int bin_mmax[STRK_PK_NBIN] = {0}, bin_flank[STRK_PK_NBIN] = {0};
     void release() {
         arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
         motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
@@ -223,7 +223,7 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     CU(cudaMalloc((void **)&ctx->d_queue, 4 * sizeof(unsigned int)));
     CU(cudaMalloc((void **)&ctx->d_acc, 4 * sizeof(double)));
     CU(cudaMalloc((void **)&ctx->d_plan, sizeof(PlanStats)));
-    CU(cudaMalloc((void **)&ctx->d_bin_off, 9 * sizeof(unsigned int)));
+    CU(cudaMalloc((void **)&ctx->d_bin_off, STRK_PK_NBIN * sizeof(unsigned int)));
     for (int k = 0; k < 3; ++k) CU(cudaEventCreate(&ctx->ev[k]));
     *out = ctx;
     return STRK_OK;
@@ -351,7 +351,8 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
 template <int R>
 static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
                            int *table, PackedDims dims, cudaStream_t st) {
-    const size_t smem = pk_smem_bytes(R, dims);
+    size_t smem = pk_smem_bytes(R, dims);
+    if (const char *env = getenv("STRK_PK_EXTRA_SMEM")) smem += (size_t)atoi(env);  // occupancy experiments only
     static size_t configured = 0;
     if (smem > configured) {
         CU(cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -379,14 +380,12 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
 static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
                          int *table, PackedDims dims, cudaStream_t st) {
     switch (R) {
-        case 2: return launch_packed_r<2>(ctx, fams, list, n, arena, table, dims, st);
-        case 4: return launch_packed_r<4>(ctx, fams, list, n, arena, table, dims, st);
-        case 6: return launch_packed_r<6>(ctx, fams, list, n, arena, table, dims, st);
-        case 8: return launch_packed_r<8>(ctx, fams, list, n, arena, table, dims, st);
-        case 10: return launch_packed_r<10>(ctx, fams, list, n, arena, table, dims, st);
-        case 12: return launch_packed_r<12>(ctx, fams, list, n, arena, table, dims, st);
-        case 14: return launch_packed_r<14>(ctx, fams, list, n, arena, table, dims, st);
-        default: return launch_packed_r<16>(ctx, fams, list, n, arena, table, dims, st);
+#define PK_CASE(N) \
+    case N: return launch_packed_r<N>(ctx, fams, list, n, arena, table, dims, st);
+        PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8) PK_CASE(9) PK_CASE(10) PK_CASE(11)
+        PK_CASE(12) PK_CASE(13) PK_CASE(14) PK_CASE(15) PK_CASE(16)
+#undef PK_CASE
+        default: return set_err(STRK_ERR_ARG, "packed kernel: no instantiation for %d rows per lane", R);
     }
 }
 
@@ -425,7 +424,7 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     b->n_loci = n_loci;
     b->h_read_begin.assign(read_begin, read_begin + n_loci + 1);
     b->n_general = 0;
-    for (int k = 0; k < 9; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
+    for (int k = 0; k < STRK_PK_NBIN; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
     b->max_n1 = b->mb_cols_base = b->mb_m = 0;
 
     cudaStream_t st = ctx->stream;
@@ -488,12 +487,12 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
         return set_err(STRK_ERR_ARG, "batch: %s %lld %s", kind >= PLAN_ERR_MOTIF_EMPTY ? "locus" : "read", idx,
                        what[kind <= 8 ? kind : 0]);
     }
-    // segment offsets: general first, then packed classes from R = 16 down to 2
-    unsigned off[9];
+    // segment offsets: general first, then packed classes from R = 16 down to 2 (class 1 stays empty)
+    unsigned off[STRK_PK_NBIN];
     unsigned acc = hp.bin_cnt[0];
     off[0] = 0;
     b->n_general = hp.bin_cnt[0];
-    for (int k = 8; k >= 1; --k) {
+    for (int k = STRK_PK_RMAX; k >= 1; --k) {
         off[k] = acc;
         b->bin_off[k] = acc;
         b->bin_cnt[k] = hp.bin_cnt[k];
@@ -597,9 +596,11 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                 return set_err(STRK_ERR_NOMEM, "cannot allocate the fallback list");
             }
             CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
-            for (int k = 8; k >= 1; --k) {
+            // one launch per rows-per-lane class, back to back on the run's stream (spreading the classes over
+            // several streams was measured slower: concurrent grids with different footprints fragment the SMs)
+            for (int k = STRK_PK_RMAX; k >= 1; --k) {
                 if (!b->bin_cnt[k]) continue;
-                const int R = 2 * k;
+                const int R = k;
                 PackedDims dims;
                 dims.colt_entries = b->bin_flank[k] + 64;
                 dims.prof_words = b->bin_mmax[k] * R * 32;
@@ -806,22 +807,22 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
         if (rc) return rc;
     } else {
         // same routing as strk_batch_run: packed kernel per R, the rest (and its fallbacks) to the general kernel
-        std::vector<int> lists[9];
-        int mmax[9] = {0}, flank[9] = {0}, wmax[9] = {0};
+        std::vector<int> lists[STRK_PK_NBIN];
+        int mmax[STRK_PK_NBIN] = {0}, flank[STRK_PK_NBIN] = {0}, wmax[STRK_PK_NBIN] = {0};
         for (int64_t r = 0; r < n_reads; ++r) {
             const FamDesc &f = fams[(size_t)r];
             int R = strk_pick_rows_packed(f.n_fl + f.n_tr + f.n_fr + 1);
             if (f.n_fl < 1 || f.n_fr < 1 || f.n_fl > PK_FLANK_MAX || f.n_fr > PK_FLANK_MAX || f.m * R > 128 ||
                 f.n_hi - f.n_lo + 1 > 64)
                 R = 0;
-            lists[R / 2].push_back((int)r);
-            mmax[R / 2] = std::max(mmax[R / 2], f.m);
-            flank[R / 2] = std::max(flank[R / 2], std::max(f.n_fl, f.n_fr));
-            wmax[R / 2] = std::max(wmax[R / 2], f.n_hi - f.n_lo + 1);
+            lists[R].push_back((int)r);
+            mmax[R] = std::max(mmax[R], f.m);
+            flank[R] = std::max(flank[R], std::max(f.n_fl, f.n_fr));
+            wmax[R] = std::max(wmax[R], f.n_hi - f.n_lo + 1);
         }
         std::vector<int> flat;
-        size_t offs[9];
-        for (int k = 0; k < 9; ++k) {
+        size_t offs[STRK_PK_NBIN];
+        for (int k = 0; k < STRK_PK_NBIN; ++k) {
             offs[k] = flat.size();
             flat.insert(flat.end(), lists[k].begin(), lists[k].end());
         }
@@ -832,19 +833,19 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
         if (e != cudaSuccess) return set_err(STRK_ERR_NOMEM, "%s: %s", who, cudaGetErrorString(e));
         CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), ctx->stream));
         long long n_packed = 0;
-        for (int k = 8; k >= 1; --k) {
+        for (int k = STRK_PK_RMAX; k >= 1; --k) {
             if (lists[k].empty()) continue;
             PackedDims dims;
             dims.colt_entries = flank[k] + 64;
-            dims.prof_words = mmax[k] * 2 * k * 32;
+            dims.prof_words = mmax[k] * k * 32;
             dims.w_max = (wmax[k] + 3) / 4 * 4;
-            if (pk_smem_bytes(2 * k, dims) > 200 * 1024) {
+            if (pk_smem_bytes(k, dims) > 200 * 1024) {
                 rc = launch_general(ctx, false, d_fams, d_lists + offs[k], (long long)lists[k].size(), d_arena, d_table,
                                     b_len, rowlen, ctx->stream);
                 if (rc) return rc;
                 continue;
             }
-            rc = launch_packed(ctx, 2 * k, d_fams, d_lists + offs[k], (int)lists[k].size(), d_arena, (int *)d_table, dims,
+            rc = launch_packed(ctx, k, d_fams, d_lists + offs[k], (int)lists[k].size(), d_arena, (int *)d_table, dims,
                                ctx->stream);
             if (rc) return rc;
             n_packed += (long long)lists[k].size();

@@ -39,7 +39,12 @@
 #include "strk_common.cuh"
 
 #define PK_FLANK_MAX 160  // longest flank the packed kernel stages (reference default flank_size = 70)
-#define PK_WARPS 4        // warps (= reads in flight) per CTA
+#ifndef PK_WARPS
+#define PK_WARPS 4  // warps (= reads in flight) per CTA
+#endif
+#ifndef PK_MIN_CTAS  // occupancy the register allocation is held to (shared memory allows about as many)
+#define PK_MIN_CTAS(R) ((R) <= 10 ? 5 : 4)
+#endif
 
 struct PackedDims {
     int colt_entries;  // uint4 entries of the per-column table  (>= max flank + 64)
@@ -77,6 +82,14 @@ __device__ __forceinline__ unsigned pk_add(unsigned a, unsigned b, unsigned one)
     return r;
 }
 
+// H = max3(t, u, H) with the destination tied to the H register (keeps ptxas from renaming it and moving it back)
+__device__ __forceinline__ void pk_max3_inplace(unsigned &h, unsigned t, unsigned u) {
+    asm("{.reg .b32 t1; \n\t"
+        "max.u16x2 t1, %1, %2; \n\t"
+        "max.u16x2 %0, t1, %0;}\n\t"
+        : "+r"(h) : "r"(t), "r"(u));
+}
+
 // Per-lane state of one read in flight.  Everything is indexed with compile-time constants after unrolling,
 // so the arrays live in registers.
 template <int R>
@@ -87,8 +100,28 @@ struct PkState {
     unsigned prev_up, topv, pm;
     int poff;       // word offset of the current profile column (motif phase)
     int cand_step;  // step at which this lane reaches the next forward candidate column
-    uint4 *dstF;    // next forward capture slot (lane-offset applied)
+    unsigned foff;  // next forward capture slot: uint4 index into the warp's scratch (lane offset applied)
 };
+
+// One column of the wavefront -> scratch: H[0..R) and the prefix-max word, as QN 128-bit stores.  The words after
+// the prefix maximum are never read; they are filled with DISTINCT live registers so that ptxas can keep the last
+// quad in place (a duplicated register would force copies before the vector store).
+template <int R>
+__device__ __forceinline__ void pk_capture(const PkState<R> &st, uint4 *__restrict__ dst, const unsigned on) {
+    constexpr int QN = (R + 1 + 3) / 4;
+    const unsigned fill[4] = {st.pm, st.prev_up, st.topv, st.foff};
+#pragma unroll
+    for (int q = 0; q < QN; ++q) {
+        uint4 v;
+        v.x = 4 * q + 0 < R ? st.H[(4 * q + 0) % R] : fill[(4 * q + 0 - R) & 3];
+        v.y = 4 * q + 1 < R ? st.H[(4 * q + 1) % R] : fill[(4 * q + 1 - R) & 3];
+        v.z = 4 * q + 2 < R ? st.H[(4 * q + 2) % R] : fill[(4 * q + 2 - R) & 3];
+        v.w = 4 * q + 3 < R ? st.H[(4 * q + 3) % R] : fill[(4 * q + 3 - R) & 3];
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"l"(dst + q * 32),
+                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(on)
+                     : "memory");
+    }
+}
 
 // FLANK1R = one-table path during the ramp-up steps: lanes that have not reached column 1 yet must see a
 // zero score, so their addend is masked off
@@ -101,7 +134,7 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
                                        const unsigned one, const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ ctp,
                                        const unsigned *__restrict__ prof_lane, const int pstride, const int pwrap,
                                        const int m, const int last_cand_step, const int bstep,
-                                       uint4 *__restrict__ dstB) {
+                                       uint4 *__restrict__ scr, uint4 *__restrict__ dstB) {
     constexpr int QN = (R + 1 + 3) / 4;
 #pragma unroll 1
     for (; s < s_end; ++s) {
@@ -112,73 +145,68 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
         st.prev_up = up_in;
         if (CORE == PK_CORE_PROF) {
             const unsigned *pp = prof_lane + st.poff;
+            unsigned t[R];
+            t[0] = d + pp[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) t[r] = st.H[r - 1] + pp[r * 32];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const unsigned left = st.H[r];
-                const unsigned h = __vimax3_u16x2(d + pp[r * 32], u, left);
-                d = left;
-                u = h;
-                st.H[r] = h;
+                pk_max3_inplace(st.H[r], t[r], u);
+                u = st.H[r];
             }
             st.poff = st.poff + pstride == pwrap ? 0 : st.poff + pstride;
         } else {
             const uint4 ct = ctp[s];  // = colT[column + 31]
             const unsigned started = s >= lane ? one : 0u;
+            unsigned t[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const unsigned left = st.H[r];
-                unsigned t;
+                const unsigned dd = r == 0 ? d : st.H[r == 0 ? 0 : r - 1];
                 if (CORE == PK_CORE_FLANK1)
-                    t = pk_add(pk_add(d, pk_prmt(ct.x, ct.z, st.selA[r]), one), st.selB[r], one);
+                    t[r] = pk_add(pk_add(dd, pk_prmt(ct.x, ct.z, st.selA[r]), one), st.selB[r], one);
                 else if (CORE == PK_CORE_FLANK1R)  // addend * (0 | 1): masked on the FMA pipe as well
-                    t = pk_add(st.selB[r], pk_add(d, pk_prmt(ct.x, ct.z, st.selA[r]), one), started);
+                    t[r] = pk_add(st.selB[r], pk_add(dd, pk_prmt(ct.x, ct.z, st.selA[r]), one), started);
                 else
-                    t = pk_add(pk_add(d, pk_prmt(ct.x, ct.y, st.selA[r]), one), pk_prmt(ct.z, ct.w, st.selB[r]), one);
-                const unsigned h = __vimax3_u16x2(t, u, left);
-                d = left;
-                u = h;
-                st.H[r] = h;
+                    t[r] = pk_add(pk_add(dd, pk_prmt(ct.x, ct.y, st.selA[r]), one), pk_prmt(ct.z, ct.w, st.selB[r]), one);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                pk_max3_inplace(st.H[r], t[r], u);
+                u = st.H[r];
             }
         }
         st.pm = __viaddmax_u16x2(st.pm, ginc, st.H[R - 1]);
+#ifdef PK_BRANCHY_CAPTURE
         if (FC) {
             if (s == st.cand_step) {
-#pragma unroll
-                for (int q = 0; q < QN; ++q) {
-                    uint4 v;
-                    v.x = 4 * q + 0 < R ? st.H[(4 * q + 0) % R] : st.pm;
-                    v.y = 4 * q + 1 < R ? st.H[(4 * q + 1) % R] : st.pm;
-                    v.z = 4 * q + 2 < R ? st.H[(4 * q + 2) % R] : st.pm;
-                    v.w = 4 * q + 3 < R ? st.H[(4 * q + 3) % R] : st.pm;
-                    st.dstF[q * 32] = v;
-                }
-                st.dstF += QN * 32;
+                pk_capture<R>(st, scr + st.foff, 1u);
+                st.foff += QN * 32;
                 st.cand_step = st.cand_step + m > last_cand_step ? 0x7fffffff : st.cand_step + m;
             }
         }
         if (BC) {
-            if (s == bstep) {
-#pragma unroll
-                for (int q = 0; q < QN; ++q) {
-                    uint4 v;
-                    v.x = 4 * q + 0 < R ? st.H[(4 * q + 0) % R] : st.pm;
-                    v.y = 4 * q + 1 < R ? st.H[(4 * q + 1) % R] : st.pm;
-                    v.z = 4 * q + 2 < R ? st.H[(4 * q + 2) % R] : st.pm;
-                    v.w = 4 * q + 3 < R ? st.H[(4 * q + 3) % R] : st.pm;
-                    dstB[q * 32] = v;
-                }
-            }
+            if (s == bstep) pk_capture<R>(st, dstB, 1u);
         }
+#else
+        if (FC) {  // predicated, not branched: some lane captures in almost every step of the candidate region
+            const bool hit = s == st.cand_step;
+            pk_capture<R>(st, scr + st.foff, hit ? 1u : 0u);
+            const int nxt = st.cand_step + m;
+            st.foff += hit ? QN * 32 : 0;
+            st.cand_step = hit ? (nxt > last_cand_step ? 0x7fffffff : nxt) : st.cand_step;
+        }
+        if (BC) pk_capture<R>(st, dstB, s == bstep ? 1u : 0u);
+#endif
     }
 }
 
 template <int R>
-__global__ void __launch_bounds__(PK_WARPS * 32, R <= 10 ? 5 : 4)
+__global__ void __launch_bounds__(PK_WARPS * 32, PK_MIN_CTAS(R))
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
                  int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
                  int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count) {
-    static_assert(R % 2 == 0 && R >= 2 && R <= 16, "R must be even");
+    static_assert(R >= 2 && R <= STRK_PK_RMAX, "rows per lane out of range");
     constexpr int N = 32 * R;
     constexpr int QN = (R + 1 + 3) / 4;
     extern __shared__ uint4 smem_raw[];
@@ -361,7 +389,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         st.topv = 0u;  // top border of the column lane 0 computes next
         st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
         st.poff = 0;
-        st.dstF = scr + lane;
+        st.foff = (unsigned)lane;
         uint4 *dstB = scr + (size_t)nW * (QN * 32) + lane;
 
         // step ranges (warp-uniform).  Lane t is at column c during step c + t - 1.
@@ -380,7 +408,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
 #define PK_RUN(CORE, FC, BC, END)                                                                          \
     pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, one, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,        \
-                            last_cand_step, bstep, dstB)
+                            last_cand_step, bstep, scr, dstB)
 
         int s = 0;
         // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
@@ -388,10 +416,18 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         {
             // part 0: ramp-up steps 0..30 (captures compiled in; they are rare this early)
             const int e0 = s_star < 31 ? s_star : 31;
-            if (one_table)
-                PK_RUN(PK_CORE_FLANK1R, true, true, e0);
-            else
-                PK_RUN(PK_CORE_FLANK2, true, true, e0);
+            const bool ramp_caps = fc_begin < e0 || bc_begin < e0;
+            if (one_table) {
+                if (ramp_caps)
+                    PK_RUN(PK_CORE_FLANK1R, true, true, e0);
+                else
+                    PK_RUN(PK_CORE_FLANK1R, false, false, e0);
+            } else {
+                if (ramp_caps)
+                    PK_RUN(PK_CORE_FLANK2, true, true, e0);
+                else
+                    PK_RUN(PK_CORE_FLANK2, false, false, e0);
+            }
             st.pm = 0u;
             // part 1: cut where the capture switches change, like the motif phase
             while (s < s_star) {

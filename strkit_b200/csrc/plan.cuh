@@ -10,9 +10,9 @@
 
 struct PlanStats {
     unsigned long long first_error;  // (index << 8 | kind), smallest wins; ~0 = none
-    unsigned bin_cnt[9];             // reads per class: [0] general kernel only, [k] packed kernel with R = 2k
-    unsigned bin_cursor[9];
-    int bin_mmax[9], bin_flank[9];
+    unsigned bin_cnt[STRK_PK_NBIN];  // reads per class: [0] general kernel only, [R] packed kernel with R rows per lane
+    unsigned bin_cursor[STRK_PK_NBIN];
+    int bin_mmax[STRK_PK_NBIN], bin_flank[STRK_PK_NBIN];
     int max_n1;
     int mb_cols_base;  // multi-pass (db > 512) reads: max of max(fl, fr) + m * est
     int mb_m;          //                              max motif length
@@ -51,9 +51,9 @@ __global__ void plan_reads_scan_kernel(const unsigned long long *__restrict__ se
                                        const int *__restrict__ motif_len, long long n_reads,
                                        unsigned long long arena_bytes, int packed_ok, unsigned char *__restrict__ bin,
                                        PlanStats *st) {
-    __shared__ unsigned s_cnt[9];
-    __shared__ int s_mmax[9], s_flank[9], s_max_n1, s_mb_cols, s_mb_m;
-    if (threadIdx.x < 9) s_cnt[threadIdx.x] = 0, s_mmax[threadIdx.x] = 0, s_flank[threadIdx.x] = 0;
+    __shared__ unsigned s_cnt[STRK_PK_NBIN];
+    __shared__ int s_mmax[STRK_PK_NBIN], s_flank[STRK_PK_NBIN], s_max_n1, s_mb_cols, s_mb_m;
+    if (threadIdx.x < STRK_PK_NBIN) s_cnt[threadIdx.x] = 0, s_mmax[threadIdx.x] = 0, s_flank[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_max_n1 = 0, s_mb_cols = 0, s_mb_m = 0;
     __syncthreads();
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +76,7 @@ __global__ void plan_reads_scan_kernel(const unsigned long long *__restrict__ se
             const int m = motif_len[read_locus[r]];
             int R = packed_ok ? strk_pick_rows_packed((int)n1 + 1) : 0;
             if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128 || m <= 0) R = 0;
-            b = R / 2;
+            b = R;
             atomicMax(&s_max_n1, (int)n1);
             if (b) {
                 atomicMax(&s_mmax[b], m);
@@ -91,7 +91,7 @@ __global__ void plan_reads_scan_kernel(const unsigned long long *__restrict__ se
         atomicAdd(&s_cnt[b], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 9) {
+    if (threadIdx.x < STRK_PK_NBIN) {
         if (s_cnt[threadIdx.x]) atomicAdd(&st->bin_cnt[threadIdx.x], s_cnt[threadIdx.x]);
         if (s_mmax[threadIdx.x]) atomicMax(&st->bin_mmax[threadIdx.x], s_mmax[threadIdx.x]);
         if (s_flank[threadIdx.x]) atomicMax(&st->bin_flank[threadIdx.x], s_flank[threadIdx.x]);
@@ -106,8 +106,8 @@ __global__ void plan_reads_scan_kernel(const unsigned long long *__restrict__ se
 // segmented work order: class k occupies order[bin_off[k] .. bin_off[k] + bin_cnt[k])
 __global__ void plan_reads_scatter_kernel(const unsigned char *__restrict__ bin, long long n_reads,
                                           const unsigned *__restrict__ bin_off, PlanStats *st, int *__restrict__ order) {
-    __shared__ unsigned s_cnt[9], s_base[9];
-    if (threadIdx.x < 9) s_cnt[threadIdx.x] = 0;
+    __shared__ unsigned s_cnt[STRK_PK_NBIN], s_base[STRK_PK_NBIN];
+    if (threadIdx.x < STRK_PK_NBIN) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int b = 0;
@@ -117,7 +117,7 @@ __global__ void plan_reads_scatter_kernel(const unsigned char *__restrict__ bin,
         local = atomicAdd(&s_cnt[b], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 9 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&st->bin_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < STRK_PK_NBIN && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&st->bin_cursor[threadIdx.x], s_cnt[threadIdx.x]);
     __syncthreads();
     if (r < n_reads) order[bin_off[b] + s_base[b] + local] = (int)r;
 }

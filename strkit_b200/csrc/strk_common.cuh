@@ -34,11 +34,13 @@ struct ScoreConsts {
     unsigned one;                              // = 1, opaque to the compiler: multiplier of the IMAD-pipe adds
 };
 
-// rows per lane of the packed kernel (even values only, 32*R >= n1); 0 = too long for it
+// rows per lane of the packed kernel (32*R >= n1, every R in 2..16 is instantiated); 0 = too long for it
+#define STRK_PK_RMAX 16
+#define STRK_PK_NBIN (STRK_PK_RMAX + 1)  // work classes of a batch: [0] general kernel only, [R] packed kernel with R rows per lane
 __host__ __device__ inline int strk_pick_rows_packed(int n1) {
-    int r = (n1 + 63) / 64 * 2;
+    int r = (n1 + 31) / 32;
     if (r < 2) r = 2;
-    return r <= 16 ? r : 0;
+    return r <= STRK_PK_RMAX ? r : 0;
 }
 
 __host__ __device__ inline int strk_pick_rows(int n1) {
