@@ -99,6 +99,16 @@ int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes,
                       const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
                       const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, strk_batch **batch);
 
+/* An empty, reusable batch and its (re)fill: strk_batch_fill replaces the contents and recycles the device
+ * buffers (no cudaMalloc once they have grown to the block size).  strk_batch_upload = create + fill.
+ * A host thread that keeps two contexts on one GPU can overlap the H2D copy of locus block i+1 (fill on
+ * context B) with the kernels of block i (run on context A): the reference's worker pool streams locus
+ * blocks the same way (strkit/call/call_sample.py:413-420). */
+int strk_batch_create(strk_ctx *ctx, strk_batch **batch);
+int strk_batch_fill(strk_ctx *ctx, strk_batch *batch, const uint8_t *arena, uint64_t arena_bytes,
+                    const uint64_t *seq_off, const int32_t *lens, const int32_t *est_cn, int64_t n_reads,
+                    const int64_t *read_begin, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci);
+
 /* Run the whole search for a resident batch: score tables (CUDA), exact replay of the reference's
  * hill-climb per locus (CUDA), widening passes for reads whose search left the table window.
  * Results stay on the device.  `stream` is a cudaStream_t (NULL = the context's own stream);

@@ -511,6 +511,21 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     return STRK_OK;
 }
 
+extern "C" int strk_batch_create(strk_ctx *ctx, strk_batch **out) {
+    if (!ctx || !out) return set_err(STRK_ERR_ARG, "strk_batch_create: null context/output");
+    *out = new (std::nothrow) strk_batch();
+    if (!*out) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    return STRK_OK;
+}
+
+extern "C" int strk_batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes,
+                               const uint64_t *seq_off, const int32_t *lens, const int32_t *est_cn, int64_t n_reads,
+                               const int64_t *read_begin, const uint64_t *motif_off, const int32_t *motif_len,
+                               int64_t n_loci) {
+    if (!ctx || !b) return set_err(STRK_ERR_ARG, "strk_batch_fill: null context/batch");
+    return batch_fill(ctx, b, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len, n_loci);
+}
+
 extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                                  const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
                                  const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci,

@@ -1,8 +1,11 @@
 """Engine: one native context (one GPU) + the calls the batcher makes across the C ABI."""
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import Iterable, Iterator
 
 import numpy as np
 
@@ -55,9 +58,19 @@ class Engine:
         self._ctx = ctx
         self.device = device
         self.end_flags = end_flags
+        self._init_args = (device, end_flags, tie_flags, mat, gap_open, gap_extend)
+        self._twin: "Engine | None" = None       # second native context on the same GPU (count_reads_stream)
+        self._stream_batch = None                # reusable strk_batch of this context
+        self._run_lock = threading.Lock()
 
     def close(self) -> None:
+        if getattr(self, "_twin", None):
+            self._twin.close()
+            self._twin = None
         if getattr(self, "_ctx", None):
+            if self._stream_batch:
+                lib.strk_batch_free(self._ctx, self._stream_batch)
+                self._stream_batch = None
             lib.strk_destroy(self._ctx)
             self._ctx = None
 
@@ -97,6 +110,46 @@ class Engine:
                                    _p(batch.motif_len), batch.n_loci, rc_params.max_iters,
                                    rc_params.initial_local_search_range, rc_params.initial_step_size, kernel, _p(out)))
         return out
+
+    def _stream_step(self, batch: ReadBatch, rc_params: RepeatCountParams, kernel: int, out: np.ndarray,
+                     run_lock: threading.Lock) -> np.ndarray:
+        """fill (H2D + device-side planning) -> run (kernels) -> download (D2H) on this context's reusable batch.
+        Only the run phase holds `run_lock`: the copies of one block overlap the kernels of the other context."""
+        if self._stream_batch is None:
+            h = C.c_void_p()
+            check(lib.strk_batch_create(self._ctx, C.byref(h)))
+            self._stream_batch = h
+        check(lib.strk_batch_fill(self._ctx, self._stream_batch, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off),
+                                  _p(batch.lens), _p(batch.est_cn), batch.n_reads, _p(batch.read_begin),
+                                  _p(batch.motif_off), _p(batch.motif_len), batch.n_loci))
+        with run_lock:
+            check(lib.strk_batch_run(self._ctx, self._stream_batch, rc_params.max_iters,
+                                     rc_params.initial_local_search_range, rc_params.initial_step_size, kernel, None))
+        check(lib.strk_batch_download(self._ctx, self._stream_batch, _p(out)))
+        return out
+
+    def count_reads_stream(self, batches: Iterable[ReadBatch], rc_params: RepeatCountParams, kernel: int = KERNEL_AUTO,
+                           outs: Iterable[np.ndarray] | None = None) -> Iterator[np.ndarray]:
+        """count_reads over a stream of locus blocks (the reference's worker pool consumes the catalog block by
+        block, call_sample.py:413-420), results yielded in block order.  Two native contexts on this GPU take
+        alternate blocks from two host threads: block i+1 is copied to the device and planned while block i is
+        in the DP kernels, so the PCIe copy disappears behind the compute.  Pin the host arrays
+        (strk_host_register / torch pinned memory) or the copies cannot overlap."""
+        if self._twin is None:
+            d, ef, tf, mat, go, ge = self._init_args
+            self._twin = Engine(d, ef, tf, mat, go, ge)
+        slots = (self, self._twin)
+        out_it = iter(outs) if outs is not None else None
+        pending: collections.deque = collections.deque()
+        with ThreadPoolExecutor(max_workers=2, thread_name_prefix="strk-stream") as pool:
+            for i, batch in enumerate(batches):
+                if len(pending) == 2:  # the slot of block i is free once block i-2 is done
+                    yield pending.popleft().result()
+                batch.validate()
+                out = next(out_it) if out_it is not None else np.empty((batch.n_reads, 4), dtype=np.int32)
+                pending.append(pool.submit(slots[i % 2]._stream_step, batch, rc_params, kernel, out, self._run_lock))
+            while pending:
+                yield pending.popleft().result()
 
     # ------------------------------------------------------------------ raw tables
     def score_tables(self, batch: ReadBatch, n_lo: np.ndarray, n_hi: np.ndarray, kernel: int = KERNEL_AUTO):

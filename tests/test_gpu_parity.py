@@ -126,6 +126,34 @@ def test_batch_config1_bit_exact(sb, oracle):
     assert np.array_equal(got_general, want) and eng.stats()["reads_packed_kernel"] == 0
 
 
+def test_count_reads_stream_matches_blocking_calls_and_oracle(sb, oracle):
+    """Streamed locus blocks (two contexts, two host threads, copies overlapped with kernels): same results,
+    in block order, as one blocking call per block; blocks of different sizes, an empty block in between."""
+    from strkit_b200 import synth
+
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    blocks = [synth.generate(synth.CONFIGS[c], n, seed=40 + i).to_host()
+              for i, (c, n) in enumerate([(1, 120), (3, 40), (1, 1), (2, 200), (1, 64), (3, 10), (2, 33)])]
+    blocks.insert(3, blocks[0].slice_loci(0, 0))  # no loci, no reads
+    eng = sb.Engine()
+    got = list(eng.count_reads_stream(blocks, params))
+    assert len(got) == len(blocks)
+    for b, g in zip(blocks, got):
+        assert g.shape == (b.n_reads, 4)
+        if b.n_reads == 0:
+            continue
+        assert np.array_equal(g, eng.count_reads(b, params))
+        want, _ = oracle.count_loci(b.arena, b.seq_off, b.lens, b.est_cn, b.read_begin, b.motif_off, b.motif_len,
+                                    n_threads=8)
+        assert np.array_equal(g, want)
+    # caller-provided output buffers are filled in place
+    outs = [np.full((b.n_reads, 4), -7, dtype=np.int32) for b in blocks]
+    for b, o, g in zip(blocks, eng.count_reads_stream(blocks, params, outs=outs), got):
+        assert np.array_equal(o, g)
+    assert all(np.array_equal(o, g) for o, g in zip(outs, got))
+    eng.close()
+
+
 def test_batch_noisy_ont_and_bad_estimates_force_widening(sb, oracle):
     """Config-3-like reads with start estimates far off: the search leaves the first table window and
     the widening passes must still reproduce the reference trajectory exactly."""
