@@ -215,7 +215,7 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
             for (int b = 1; b < 4; ++b)
                 if (matrix[class_code[c] * STRK_NSYM + b] != matrix[class_code[c] * STRK_NSYM]) one = 0;
         ctx->h_consts.one_table_ok = one;
-        ctx->h_consts.one = 1u;
+        for (int k = 0; k < 32; ++k) ctx->h_consts.one_v[k] = 1u;
     }
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&ctx->d_consts, sizeof(ScoreConsts)));

@@ -42,6 +42,12 @@
 #ifndef PK_WARPS
 #define PK_WARPS 4  // warps (= reads in flight) per CTA
 #endif
+#ifndef PK_PROF_IMAD
+#define PK_PROF_IMAD 0
+#endif
+#ifndef PK_ONE_VREG
+#define PK_ONE_VREG 0
+#endif
 #ifndef PK_MIN_CTAS  // occupancy the register allocation is held to (shared memory allows about as many)
 #define PK_MIN_CTAS(R) ((R) <= 10 ? 5 : 4)
 #endif
@@ -73,9 +79,10 @@ __device__ __forceinline__ unsigned pk_prmt(unsigned a, unsigned b, unsigned sel
     return r;
 }
 
-// a + b on the FMA pipe: IMAD with a multiplier the compiler cannot see through (`one` is loaded from the
-// constants block).  The ALU pipe (PRMT, VIMNMX3; 0.5 warp-instructions per clock per scheduler) is what bounds
-// the step loops, so every add that can move to the other pipe is taken off it.
+// a + b on the FMA pipe: IMAD with a multiplier the compiler cannot see through (`one` comes from the constants
+// block).  The ALU pipe (PRMT, VIMNMX3; 0.5 warp-instructions per clock per scheduler) bounds the flank-phase step
+// loops, so their adds are taken off it.  Variants measured in place: multiplier in a vector
+// register (PK_ONE_VREG=1) -2 %, IMAD instead of the compiler's IMAD.IADD in the motif phase (PK_PROF_IMAD=1) +0.4 %.
 __device__ __forceinline__ unsigned pk_add(unsigned a, unsigned b, unsigned one) {
     unsigned r;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
@@ -146,9 +153,15 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
         if (CORE == PK_CORE_PROF) {
             const unsigned *pp = prof_lane + st.poff;
             unsigned t[R];
+#if PK_PROF_IMAD
+            t[0] = pk_add(d, pp[0], one);
+#pragma unroll
+            for (int r = 1; r < R; ++r) t[r] = pk_add(st.H[r - 1], pp[r * 32], one);
+#else
             t[0] = d + pp[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) t[r] = st.H[r - 1] + pp[r * 32];
+#endif
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 pk_max3_inplace(st.H[r], t[r], u);
@@ -229,7 +242,11 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const int g = consts->gap;
     const int flags = consts->end_flags;
     const bool one_table_ok = consts->one_table_ok != 0;
-    const unsigned one = consts->one;
+#if PK_ONE_VREG
+    const unsigned one = consts->one_v[lane];  // per-lane load: stays in a vector register
+#else
+    const unsigned one = consts->one_v[0];  // uniform load
+#endif
     const bool s1_beg = flags & 1, s1_end = flags & 2, s2_beg = flags & 4, s2_end = flags & 8;
     const bool lane0 = lane == 0;
 

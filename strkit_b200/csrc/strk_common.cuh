@@ -31,7 +31,10 @@ struct ScoreConsts {
     unsigned char cls_of[STRK_SMAT_ROWS + 1];  // symbol code -> PRMT row class, 0x80 = not representable
     int packed_ok;                             // every biased score fits a positive byte
     int one_table_ok;                          // N / X / other rows score the same against A, C, G and T
-    unsigned one;                              // = 1, opaque to the compiler: multiplier of the IMAD-pipe adds
+    // = 1 in every entry, opaque to the compiler: multiplier of the FMA-pipe adds (IMAD d, one, s).  Read as a
+    // uniform value by default; PK_ONE_VREG=1 reads it per lane into a vector register (tuning switch: the
+    // micro-benchmark tools/ubench_pipes.cu favours the vector-register form, the real step loops do not).
+    unsigned one_v[32];
 };
 
 // rows per lane of the packed kernel (32*R >= n1, every R in 2..16 is instantiated); 0 = too long for it

@@ -37,15 +37,17 @@ __device__ __forceinline__ unsigned lds(unsigned addr) {  // volatile: keeps the
 }
 
 enum { T_MAX3 = 0, T_ADDMAX, T_PRMT, T_IMAD, T_IADD, T_LDS, T_SHFL, T_MAX3_CHAIN, T_MIX_PROF, T_MIX_FLANK, T_MAX3_IMAD,
-       T_MAX3_PRMT, T_MAX2, T_MIX_PROF_CHAIN, T_COUNT };
+       T_MAX3_PRMT, T_MAX2, T_MIX_PROF_CHAIN, T_MIX_FLANK_VREG, T_MIX_FLANK_PLAIN, T_MAX3_IMAD_VREG, T_MAX3_IADD, T_COUNT };
 static const char *names[T_COUNT] = {"VIMNMX3.U16x2 (8 indep chains)", "VIADDMNMX.U16x2 (8 indep)", "PRMT (8 indep)",
                                      "IMAD r*r+r (8 indep)", "IADD r+r via IMAD.IADD/IADD3 (8 indep)", "LDS.32 (8 indep)",
                                      "SHFL.UP (8 indep)", "VIMNMX3.U16x2 one dependent chain (latency)",
                                      "mix prof: LDS + IMAD + VIMNMX3 (8 indep cells)",
                                      "mix flank: PRMT + 2 IMAD + VIMNMX3 (8 indep cells)", "VIMNMX3 + IMAD 1:1 (8 indep)",
                                      "VIMNMX3 + PRMT 1:1 (8 indep)", "VIMNMX.U16x2 2-input (8 indep)",
-                                     "mix prof, VIMNMX3 as ONE serial chain of 8 (like the kernel)"};
-static const int inst_per_iter[T_COUNT] = {8, 8, 8, 8, 8, 8, 8, 8, 24, 32, 16, 16, 8, 24};
+                                     "mix prof, VIMNMX3 as ONE serial chain of 8 (like the kernel)",
+                                     "mix flank, multiplier in a vector register", "mix flank, plain C adds (compiler's choice)",
+                                     "VIMNMX3 + IMAD (vector-register multiplier) 1:1", "VIMNMX3 + plain add 1:1"};
+static const int inst_per_iter[T_COUNT] = {8, 8, 8, 8, 8, 8, 8, 8, 24, 32, 16, 16, 8, 24, 32, 32, 16, 16};
 
 template <int T>
 __global__ void __launch_bounds__(128) k(int iters, unsigned seed, unsigned one, unsigned *out, long long *cyc) {
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(128) k(int iters, unsigned seed, unsigned one,
     const unsigned c1 = seed | 1u, c2 = seed + 7u;
     const unsigned *sp = sm + (threadIdx.x & 31);
     unsigned off = 0;
+    const unsigned vone = out[1 + (threadIdx.x & 31)];  // = 1, in a vector register
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -111,6 +114,30 @@ __global__ void __launch_bounds__(128) k(int iters, unsigned seed, unsigned one,
                 for (int q = 0; q < 8; ++q) {
                     const unsigned t = imad(imad(b[q], one, prmt(c1, c2, a[q] & 0x7777u)), one, b[(q + 1) & 7]);
                     a[q] = max3u(t, a[q], c2);
+                }
+            } else if (T == T_MIX_FLANK_VREG) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned t = imad(imad(b[q], vone, prmt(c1, c2, a[q] & 0x7777u)), vone, b[(q + 1) & 7]);
+                    a[q] = max3u(t, a[q], c2);
+                }
+            } else if (T == T_MIX_FLANK_PLAIN) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned t = b[q] + prmt(c1, c2, a[q] & 0x7777u) + b[(q + 1) & 7];
+                    a[q] = max3u(t, a[q], c2);
+                }
+            } else if (T == T_MAX3_IMAD_VREG) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    a[q] = max3u(a[q], b[q], c1);
+                    b[q] = imad(b[q], vone, c2);
+                }
+            } else if (T == T_MAX3_IADD) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    a[q] = max3u(a[q], b[q], c1);
+                    b[q] = b[q] + a[(q + 3) & 7];
                 }
             } else if (T == T_MAX3_IMAD) {
 #pragma unroll
@@ -167,10 +194,15 @@ int main() {
     CK(cudaGetDeviceProperties(&p, 0));
     unsigned *d_out;
     long long *d_cyc;
-    CK(cudaMalloc(&d_out, 64));
+    CK(cudaMalloc(&d_out, 64 * 4));
+    {
+        unsigned h[64];
+        for (int i = 0; i < 64; ++i) h[i] = 1u;
+        CK(cudaMemcpy(d_out, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&d_cyc, 64));
     printf("%s, %d SMs\n", p.name, p.multiProcessorCount);
-    for (int w : {1, 2, 3, 4, 5, 6, 8}) {
+    for (int w : {1, 5, 8}) {
         run<T_MAX3>(w, d_out, d_cyc, p.multiProcessorCount);
         run<T_MAX2>(w, d_out, d_cyc, p.multiProcessorCount);
         run<T_ADDMAX>(w, d_out, d_cyc, p.multiProcessorCount);
@@ -185,6 +217,10 @@ int main() {
         run<T_MIX_PROF>(w, d_out, d_cyc, p.multiProcessorCount);
         run<T_MIX_PROF_CHAIN>(w, d_out, d_cyc, p.multiProcessorCount);
         run<T_MIX_FLANK>(w, d_out, d_cyc, p.multiProcessorCount);
+        run<T_MIX_FLANK_VREG>(w, d_out, d_cyc, p.multiProcessorCount);
+        run<T_MIX_FLANK_PLAIN>(w, d_out, d_cyc, p.multiProcessorCount);
+        run<T_MAX3_IMAD_VREG>(w, d_out, d_cyc, p.multiProcessorCount);
+        run<T_MAX3_IADD>(w, d_out, d_cyc, p.multiProcessorCount);
     }
     return 0;
 }
