@@ -157,6 +157,42 @@ int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, c
  *   stats[6] reads handled by the packed kernel   stats[7] reads handled by the general kernel */
 int strk_get_stats(strk_ctx *ctx, double stats[8]);
 
+/*
+ * call_alleles (strkit/call/allele.py:176-336), batched over loci: weighted bootstrap resampling of each locus'
+ * per-read copy numbers (get_resampled_bootstrapped_reads, :126-173, separate_strands = False as both call sites
+ * pass it, call_locus.py:201-214,255-268), a one- or two-component spherical Gaussian mixture per replicate
+ * (fit_gmm :56-123 over sklearn.mixture.GaussianMixture: k-means++ seeding, n_init restarts, tol 1e-3, max_iter 100,
+ * reg_covar 1e-6; the weight filters of :88-121; make_single_gaussian, gmm.py:72-80), then per-allele medians and
+ * interpolated-inverted-CDF confidence intervals over the replicates (:295-336).
+ *   cn / weights   per read, loci delimited by read_begin[n_loci + 1]; weights as the reference passes them
+ *                  (normalised per locus, call_locus.py:191-192)
+ *   out_i[l]       1 + 5 * n_alleles ints: modal_n, call[A], call_95_cis[A][2], call_99_cis[A][2]
+ *   out_d[l]       3 * n_alleles doubles: means[A], weights[A], stdevs[A]
+ *   out_status[l]  0 = bootstrapped, 1 = fewer than min_reads reads (the reference returns None),
+ *                  2 = a single distinct copy number (no bootstrap, allele.py:196-214)
+ *   ms_out         device time of the kernels (CUDA events), may be NULL
+ * The random streams are this library's (counter-based Philox keyed by seed, locus, replicate), not numpy's:
+ * results agree with the reference statistically.  n_alleles 1 and 2 are implemented.
+ */
+int strk_call_alleles(strk_ctx *ctx, const int32_t *cn, const double *weights, const int64_t *read_begin,
+                      int64_t n_loci, int n_alleles, int num_bootstrap, int min_reads, int min_allele_reads,
+                      int force_gm_filter, double expansion_ratio, int filter_factor, int n_init, uint64_t seed,
+                      int32_t *out_i, double *out_d, int32_t *out_status, double *ms_out);
+
+/* The deterministic core of the above for caller-provided replicates: problem q = K[q] distinct values
+ * x[q * kcap ..] with multiplicities counts[q * kcap ..] and n_init forced k-means++ seed pairs
+ * init[q * 2 * n_init ..] (indices into x).  out[q] = {mean0, weight0, stdev0, mean1, weight1, stdev1, n_peaks}
+ * as fit_gmm + the per-replicate bookkeeping of call_alleles (allele.py:249-293) produce them. */
+int strk_gmm_fit_counts(strk_ctx *ctx, const double *x, const int32_t *counts, const int32_t *K, const int32_t *init,
+                        int64_t n_problems, int kcap, int n_alleles, int num_bootstrap, int min_allele_reads,
+                        int force_gm_filter, double expansion_ratio, int filter_factor, int n_init, double *out);
+
+/* The aggregation step alone (allele.py:295-336): replicate arrays [locus][allele][replicate] (+ peaks
+ * [locus][replicate]) -> out_i / out_d as in strk_call_alleles. */
+int strk_alleles_aggregate(strk_ctx *ctx, const double *rep_means, const double *rep_weights, const double *rep_stdevs,
+                           const uint8_t *rep_peaks, int64_t n_loci, int n_alleles, int num_bootstrap, int32_t *out_i,
+                           double *out_d);
+
 /* Integer issue-rate micro-benchmark: the roofline denominator of the DP kernels (MEASURED_PEAKS.json has
  * no INT32 figure).  out_tiops[0] = ALU pipe only (VIADDMNMX), [1] = FMA pipe only (IMAD), [2] = both pipes;
  * units: 1e12 lane-level 32-bit integer instructions per second, all SMs. */

@@ -1136,3 +1136,8 @@ extern "C" int strk_measure_int_peak(strk_ctx *ctx, double out_tiops[3]) {
     cudaFree(d_out);
     return STRK_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// bootstrap / GMM allele calls (the consumer of the per-read counts)
+// ------------------------------------------------------------------------------------------------
+#include "alleles_api.cuh"
