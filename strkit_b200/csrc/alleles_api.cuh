@@ -82,23 +82,27 @@ extern "C" int strk_call_alleles(strk_ctx *ctx, const int32_t *cn, const double 
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int kcap = max_n, A = n_alleles, B = num_bootstrap;
-    AllDev dev;
-    int *d_cn = nullptr, *d_vals = nullptr, *d_cnt = nullptr, *d_K = nullptr, *d_n = nullptr, *d_status = nullptr,
-        *d_kmax = nullptr, *d_oi = nullptr;
-    double *d_w = nullptr, *d_cdf = nullptr, *d_od = nullptr;
-    long long *d_rb = nullptr;
-    cudaError_t e = dev.up(&d_cn, (const int *)cn, (size_t)n_reads, st);
-    if (e == cudaSuccess) e = dev.up(&d_w, weights, (size_t)n_reads, st);
-    if (e == cudaSuccess) e = dev.up(&d_rb, (const long long *)read_begin, (size_t)n_loci + 1, st);
-    if (e == cudaSuccess) e = dev.get(&d_vals, (size_t)n_loci * kcap);
-    if (e == cudaSuccess) e = dev.get(&d_cdf, (size_t)n_loci * kcap);
-    if (e == cudaSuccess) e = dev.get(&d_cnt, (size_t)n_loci * kcap);
-    if (e == cudaSuccess) e = dev.get(&d_K, (size_t)n_loci);
-    if (e == cudaSuccess) e = dev.get(&d_n, (size_t)n_loci);
-    if (e == cudaSuccess) e = dev.get(&d_status, (size_t)n_loci);
-    if (e == cudaSuccess) e = dev.get(&d_kmax, 1);
-    if (e == cudaSuccess) e = dev.get(&d_oi, (size_t)n_loci * (1 + 5 * A));
-    if (e == cudaSuccess) e = dev.get(&d_od, (size_t)n_loci * 3 * A);
+    // context-owned buffers, recycled across calls (no cudaMalloc / cudaFree in the steady state)
+    cudaError_t e = cudaSuccess;
+    auto take_i = [&](int slot, size_t n) -> int * {
+        if (e == cudaSuccess) e = ctx->al_i[slot].reserve(n ? n : 1);
+        return ctx->al_i[slot].p;
+    };
+    auto take_d = [&](int slot, size_t n) -> double * {
+        if (e == cudaSuccess) e = ctx->al_d[slot].reserve(n ? n : 1);
+        return ctx->al_d[slot].p;
+    };
+    int *d_cn = take_i(0, (size_t)n_reads), *d_vals = take_i(1, (size_t)n_loci * kcap);
+    int *d_cnt = take_i(2, (size_t)n_loci * kcap), *d_K = take_i(3, (size_t)n_loci), *d_n = take_i(4, (size_t)n_loci);
+    int *d_status = take_i(5, (size_t)n_loci), *d_kmax = take_i(6, 1), *d_oi = take_i(7, (size_t)n_loci * (1 + 5 * A));
+    double *d_w = take_d(0, (size_t)n_reads), *d_cdf = take_d(1, (size_t)n_loci * kcap);
+    double *d_od = take_d(2, (size_t)n_loci * 3 * A);
+    if (e == cudaSuccess) e = ctx->al_rb.reserve((size_t)n_loci + 1);
+    long long *d_rb = ctx->al_rb.p;
+    if (e == cudaSuccess && n_reads) e = cudaMemcpyAsync(d_cn, cn, (size_t)n_reads * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_reads) e = cudaMemcpyAsync(d_w, weights, (size_t)n_reads * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_rb, read_begin, ((size_t)n_loci + 1) * sizeof(long long), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "strk_call_alleles: %s", cudaGetErrorString(e));
@@ -115,21 +119,19 @@ extern "C" int strk_call_alleles(strk_ctx *ctx, const int32_t *cn, const double 
     int kmax = 0;
     CU(cudaMemcpyAsync(&kmax, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    // replicate estimates, in chunks of loci that keep the scratch near 1 GB
+    // replicate estimates, in chunks of loci that keep the scratch near 256 MB (context-owned, recycled across calls)
     const size_t per_locus = (size_t)A * B * 3 * sizeof(double) + (size_t)B;
-    int64_t chunk = (int64_t)((size_t)1 << 30) / (int64_t)per_locus;
+    int64_t chunk = (int64_t)((size_t)1 << 28) / (int64_t)per_locus;
     if (chunk < 1) chunk = 1;
     if (chunk > n_loci) chunk = n_loci;
-    double *rm = nullptr, *rw = nullptr, *rs = nullptr;
-    unsigned char *rp = nullptr;
-    e = dev.get(&rm, (size_t)chunk * A * B);
-    if (e == cudaSuccess) e = dev.get(&rw, (size_t)chunk * A * B);
-    if (e == cudaSuccess) e = dev.get(&rs, (size_t)chunk * A * B);
-    if (e == cudaSuccess) e = dev.get(&rp, (size_t)chunk * B);
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = ctx->al_rep[k].reserve((size_t)chunk * A * B);
+    if (e == cudaSuccess) e = ctx->al_peaks.reserve((size_t)chunk * B);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "strk_call_alleles: %s", cudaGetErrorString(e));
     }
+    double *rm = ctx->al_rep[0].p, *rw = ctx->al_rep[1].p, *rs = ctx->al_rep[2].p;
+    unsigned char *rp = ctx->al_peaks.p;
     int np2 = 1;
     while (np2 < B) np2 <<= 1;
     const size_t agg_smem = (size_t)np2 * (sizeof(double) + sizeof(int));

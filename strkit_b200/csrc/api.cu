@@ -88,6 +88,11 @@ struct strk_ctx {
     DevBuf<long long> list_c;
     DevBuf<int> fallback;            // reads the packed kernel handed to the general kernel
     DevBuf<uint4> pk_scratch;        // captured DP columns of the packed kernel (per resident warp)
+    DevBuf<double> al_rep[3];        // allele calling: replicate means / weights / stdevs of one chunk of loci
+    DevBuf<unsigned char> al_peaks;  //                 replicate peak counts
+    DevBuf<int> al_i[8];             //                 per-read / per-locus integer arrays (recycled across calls)
+    DevBuf<double> al_d[3];
+    DevBuf<long long> al_rb;
     unsigned int *d_queue = nullptr;  // [0] work queue, [1] miss counter
     double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
     PlanStats *d_plan = nullptr;      // device-side planning counters
@@ -246,6 +251,11 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     ctx->list_c.release();
     ctx->fallback.release();
     ctx->pk_scratch.release();
+    for (int k = 0; k < 3; ++k) ctx->al_rep[k].release();
+    ctx->al_peaks.release();
+    for (int k = 0; k < 8; ++k) ctx->al_i[k].release();
+    for (int k = 0; k < 3; ++k) ctx->al_d[k].release();
+    ctx->al_rb.release();
     if (ctx->d_consts) cudaFree(ctx->d_consts);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     if (ctx->d_acc) cudaFree(ctx->d_acc);

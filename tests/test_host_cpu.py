@@ -116,3 +116,13 @@ def test_install_rebinds_strkit_names(monkeypatch):
     assert loc.get_repeat_count is ours.get_repeat_count and rep.get_ref_repeat_count is ours.get_ref_repeat_count
     strkit_b200.uninstall()
     assert loc.get_repeat_count() == "reference" and rep.get_ref_repeat_count() == "reference"
+    # opt-in: call_alleles (allele.py:176, from-imported at call_locus.py:28)
+    al = types.ModuleType("strkit.call.allele")
+    al.call_alleles = loc.call_alleles = lambda *a, **k: "reference"
+    monkeypatch.setitem(sys.modules, "strkit.call.allele", al)
+    assert len(strkit_b200.install()) == 4 and loc.call_alleles() == "reference"
+    strkit_b200.uninstall()
+    patched = strkit_b200.install(alleles=True)
+    assert len(patched) == 6 and loc.call_alleles is strkit_b200.call_alleles and al.call_alleles is strkit_b200.call_alleles
+    strkit_b200.uninstall()
+    assert loc.call_alleles() == "reference" and al.call_alleles() == "reference"
