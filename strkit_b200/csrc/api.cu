@@ -628,7 +628,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                 const int R = k;
                 PackedDims dims;
                 dims.colt_entries = b->bin_flank[k] + 64;
-                dims.prof_words = b->bin_mmax[k] * R * 32;
+                dims.prof_words = pk_prof_words(R, b->bin_mmax[k]);
                 dims.w_max = (W + 3) / 4 * 4;
                 if (pk_smem_bytes(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
@@ -862,7 +862,7 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
             if (lists[k].empty()) continue;
             PackedDims dims;
             dims.colt_entries = flank[k] + 64;
-            dims.prof_words = mmax[k] * k * 32;
+            dims.prof_words = pk_prof_words(k, mmax[k]);
             dims.w_max = (wmax[k] + 3) / 4 * 4;
             if (pk_smem_bytes(k, dims) > 200 * 1024) {
                 rc = launch_general(ctx, false, d_fams, d_lists + offs[k], (long long)lists[k].size(), d_arena, d_table,

@@ -59,6 +59,10 @@ struct PackedDims {
 };
 
 __host__ __device__ inline int pk_quads(int R) { return (R + 1 + 3) / 4; }  // H[0..R) + the prefix-max word
+// Packed profile of the motif phase: rows in pairs, prof[((k * RH + r / 2) * 32 + lane) * 2 + (r & 1)], so that a
+// step fetches its R scores with RH = ceil(R / 2) conflict-free LDS.64 instead of R LDS.32.
+__host__ __device__ inline int pk_prof_rows(int R) { return (R + 1) / 2 * 2; }
+__host__ __device__ inline int pk_prof_words(int R, int m) { return m * pk_prof_rows(R) * 32; }
 __host__ __device__ inline size_t pk_scratch_words_per_warp(int R, int w_max) {
     return (size_t)(w_max + 1) * pk_quads(R) * 32 * 4;
 }
@@ -151,16 +155,23 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
         unsigned d = st.prev_up, u = up_in;
         st.prev_up = up_in;
         if (CORE == PK_CORE_PROF) {
-            const unsigned *pp = prof_lane + st.poff;
+            const uint2 *pp = (const uint2 *)prof_lane + st.poff;  // this lane's row pairs of the current column
+            unsigned sc[(R + 1) / 2 * 2];
+#pragma unroll
+            for (int q = 0; q < (R + 1) / 2; ++q) {
+                const uint2 v = pp[q * 32];
+                sc[2 * q] = v.x;
+                sc[2 * q + 1] = v.y;
+            }
             unsigned t[R];
 #if PK_PROF_IMAD
-            t[0] = pk_add(d, pp[0], one);
+            t[0] = pk_add(d, sc[0], one);
 #pragma unroll
-            for (int r = 1; r < R; ++r) t[r] = pk_add(st.H[r - 1], pp[r * 32], one);
+            for (int r = 1; r < R; ++r) t[r] = pk_add(st.H[r - 1], sc[r], one);
 #else
-            t[0] = d + pp[0];
+            t[0] = d + sc[0];
 #pragma unroll
-            for (int r = 1; r < R; ++r) t[r] = st.H[r - 1] + pp[r * 32];
+            for (int r = 1; r < R; ++r) t[r] = st.H[r - 1] + sc[r];
 #endif
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -222,6 +233,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     static_assert(R >= 2 && R <= STRK_PK_RMAX, "rows per lane out of range");
     constexpr int N = 32 * R;
     constexpr int QN = (R + 1 + 3) / 4;
+    constexpr int RH = (R + 1) / 2;  // row pairs of the packed profile
     extern __shared__ uint4 smem_raw[];
     __shared__ SmemConsts sc;
     __shared__ unsigned long long t8f[STRK_NSYM_], t8b[STRK_NSYM_];
@@ -280,7 +292,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
         // ---- eligibility (warp-uniform): anything odd goes to the general kernel
         bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 64 <= dims.colt_entries &&
-                  m * R * 32 <= dims.prof_words && m <= 128 && nW <= dims.w_max &&
+                  pk_prof_words(R, m) <= dims.prof_words && m <= 128 && nW <= dims.w_max &&
                   (g * (N + ncols + 40) + 2 * N + 1024) < 65535;
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) {
@@ -355,13 +367,14 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         // column is A/C/G/T (a non-ACGT row then scores the same in every column), or no row needs an addend
         // that depends on the column (only the pad rows have one, and theirs never does)
         const bool one_table = (one_table_ok && cols_acgt) || __all_sync(0xffffffffu, rows_plain);
-        // ---- packed profile for the motif phase: prof[(k * R + r) * 32 + lane], column j = Lmax + 1 + k (mod m)
+        // ---- packed profile for the motif phase (row pairs, see pk_prof_rows), column j = Lmax + 1 + k (mod m)
         if (one_table_ok && motif_acgt) {
             for (int k = 0; k < m; ++k) {
                 const unsigned tf = (unsigned)t8f[mcodes[mod_m(k + Lmax - f.n_fl)]];
                 const unsigned tb = (unsigned)t8b[mcodes[m - 1 - mod_m(k + Lmax - f.n_fr)]];
 #pragma unroll
-                for (int r = 0; r < R; ++r) prof[(k * R + r) * 32 + lane] = pk_prmt(tf, tb, st.selA[r]) + st.selB[r];
+                for (int r = 0; r < R; ++r)
+                    prof[((k * RH + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = pk_prmt(tf, tb, st.selA[r]) + st.selB[r];
             }
         } else {
             for (int k = 0; k < m; ++k) {
@@ -371,7 +384,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 for (int r = 0; r < R; ++r) {
                     const int vf = sc.smat[((cls[r] >> 8) & 0xff) * STRK_NSYM_ + sf] + g2;
                     const int vb = sc.smat[((cls[r] >> 16) & 0xff) * STRK_NSYM_ + sb] + g2;
-                    prof[(k * R + r) * 32 + lane] = (unsigned)vf | ((unsigned)vb << 16);
+                    prof[((k * RH + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = (unsigned)vf | ((unsigned)vb << 16);
                 }
             }
         }
@@ -419,8 +432,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         const int last_cand_step = colsF + lane - 1;
         const int bstep = colsB + lane - 1;
         const uint4 *ctp = colT + 32 - lane;  // ctp[s] = table of the column this lane computes in step s
-        const unsigned *prof_lane = prof + lane;
-        const int pstride = R * 32, pwrap = m * R * 32;
+        const unsigned *prof_lane = prof + 2 * lane;
+        const int pstride = RH * 32, pwrap = m * RH * 32;  // in row pairs (uint2)
         __syncwarp();
 
 #define PK_RUN(CORE, FC, BC, END)                                                                          \
