@@ -199,9 +199,7 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
                 if (v < 0 || v > 127) ok = 0;
                 tf |= (unsigned long long)(v & 0xff) << (8 * c);
             }
-            tb = tf;
-            tf |= (unsigned long long)((end_flags & STRK_S2_BEG_FREE) ? 2 * gap_open : 0) << 56;
-            tb |= (unsigned long long)((end_flags & STRK_S2_END_FREE) ? 2 * gap_open : 0) << 56;
+            tb = tf;  // byte 7 (pad rows) stays 0: pad rows copy the row above them (dp_packed.cuh, borders)
             ctx->h_consts.t8f[b] = tf;
             ctx->h_consts.t8b[b] = tb;
         }

@@ -28,9 +28,9 @@
 // of the backward half) are captured with predicated 128-bit stores into a per-warp scratch that stays in
 // L2; the combine pass reads them back.
 //
-// Rows are front-padded to 32*R (> n1, so there is always at least one pad row, which doubles as DP row 0)
-// with a pad class whose score reproduces the border row (see dp_general.cuh); row n1 is therefore always
-// the last register of lane 31.
+// Rows are front-padded to 32*R (> n1, so there is always at least one pad row, which doubles as DP row 0);
+// row n1 is therefore always the last register of lane 31.  Pad rows score zero and so copy the row above them;
+// lane 0 injects DP row 0 above its first register (see "borders" in the kernel).
 //
 // Reads this kernel cannot take (IUPAC codes inside the read, value range beyond u16, empty flank) are
 // appended to a fallback list that the general int32 kernel processes afterwards -- still on the GPU.
@@ -136,7 +136,8 @@ __device__ __forceinline__ void pk_capture(const PkState<R> &st, uint4 *__restri
 
 // FLANK1R = one-table path during the ramp-up steps: lanes that have not reached column 1 yet must see a
 // zero score, so their addend is masked off
-enum { PK_CORE_FLANK2 = 0, PK_CORE_FLANK1 = 1, PK_CORE_PROF = 2, PK_CORE_FLANK1R = 3 };
+// FLANK0 = one-table path of a read whose rows are all A/C/G/T (or pad): no addend at all, PRMT + IMAD + VIMNMX3
+enum { PK_CORE_FLANK2 = 0, PK_CORE_FLANK1 = 1, PK_CORE_PROF = 2, PK_CORE_FLANK1R = 3, PK_CORE_FLANK0 = 4 };
 
 // Steps [s, s_end) of the wavefront; lane t computes column s - t + 1 in step s.  CORE selects the score
 // source, FC / BC switch the predicated captures of forward candidate columns / the final backward column on.
@@ -186,7 +187,9 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned dd = r == 0 ? d : st.H[r == 0 ? 0 : r - 1];
-                if (CORE == PK_CORE_FLANK1)
+                if (CORE == PK_CORE_FLANK0)
+                    t[r] = pk_add(dd, pk_prmt(ct.x, ct.z, st.selA[r]), one);
+                else if (CORE == PK_CORE_FLANK1)
                     t[r] = pk_add(pk_add(dd, pk_prmt(ct.x, ct.z, st.selA[r]), one), st.selB[r], one);
                 else if (CORE == PK_CORE_FLANK1R)  // addend * (0 | 1): masked on the FMA pipe as well
                     t[r] = pk_add(st.selB[r], pk_add(dd, pk_prmt(ct.x, ct.z, st.selA[r]), one), started);
@@ -270,7 +273,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const unsigned tinc = (s2_beg ? (unsigned)g : 0u) | ((s2_end ? (unsigned)g : 0u) << 16);
     const unsigned ginc = (unsigned)g | ((unsigned)g << 16);
     const int g2 = 2 * g;
-    const int padF = s2_beg ? STRK_PAD_FREE : STRK_PAD_PEN, padB = s2_end ? STRK_PAD_FREE : STRK_PAD_PEN;
+    const int padF = STRK_PAD_PEN, padB = STRK_PAD_PEN;  // biased score 0 in every mode: pad rows copy (see borders)
 
     for (int fam_idx = warp_global; fam_idx < n_list; fam_idx += total_warps) {
         const int fam_id = list[fam_idx];
@@ -364,9 +367,10 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             continue;
         }
         // one table per step is enough when the column-independent addend is exact: either every flank-phase
-        // column is A/C/G/T (a non-ACGT row then scores the same in every column), or no row needs an addend
-        // that depends on the column (only the pad rows have one, and theirs never does)
-        const bool one_table = (one_table_ok && cols_acgt) || __all_sync(0xffffffffu, rows_plain);
+        // column is A/C/G/T (a non-ACGT row then scores the same in every column), or no row carries an addend
+        // (rows all A/C/G/T or pad) -- in which case the step is PRMT + IMAD + VIMNMX3 per cell pair (FLANK0)
+        const bool no_addend = __all_sync(0xffffffffu, rows_plain);
+        const bool one_table = (one_table_ok && cols_acgt) || no_addend;
         // ---- packed profile for the motif phase (row pairs, see pk_prof_rows), column j = Lmax + 1 + k (mod m)
         if (one_table_ok && motif_acgt) {
             for (int k = 0; k < m; ++k) {
@@ -396,27 +400,31 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             }
         }
 
-        // ---- borders (biased by g * (row + col))
+        // ---- borders (biased by g * (row + col)).  Pad rows are COPY rows: their score byte is zero, so with
+        // up' >= diag' and up' >= left' (biased values never decrease along a row or down a column) each one
+        // repeats the value above it; lane 0 injects, as the row above its first register, DP row 0 with the bias
+        // of the LAST pad row (index off), which is therefore what every pad row holds and what the first real row
+        // reads as its up / diagonal neighbour.  No addend, whatever the begin / end mode.
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int I = lane * R + r + 1, i = I - off;
-            int bf = 0, bb = 0;  // unbiased column-0 values
+            int vf = g * off, vb = g * off;  // pad rows: DP row 0 at column 0, biased as row `off`
             if (i >= 1) {
-                bf = s1_beg ? 0 : -g * i;
-                bb = s1_end ? (i == n1 ? -g : 0) : -g * i;
+                vf = (s1_beg ? 0 : -g * i) + g * I;
+                vb = (s1_end ? (i == n1 ? -g : 0) : -g * i) + g * I;
             }
-            st.H[r] = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
+            st.H[r] = (unsigned)vf | ((unsigned)vb << 16);
         }
         {
             const int I = lane * R, i = I - off;
-            int bf = 0, bb = 0;
+            int vf = g * off, vb = g * off;
             if (i >= 1) {
-                bf = s1_beg ? 0 : -g * i;
-                bb = s1_end ? 0 : -g * i;  // i < n1 here
+                vf = (s1_beg ? 0 : -g * i) + g * I;
+                vb = (s1_end ? 0 : -g * i) + g * I;  // i < n1 here
             }
-            st.prev_up = (unsigned)(bf + g * I) | ((unsigned)(bb + g * I) << 16);
+            st.prev_up = (unsigned)vf | ((unsigned)vb << 16);
         }
-        st.topv = 0u;  // top border of the column lane 0 computes next
+        st.topv = (unsigned)(g * off) | ((unsigned)(g * off) << 16);  // DP row 0 at column 0 (then + tinc per column)
         st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
         st.poff = 0;
         st.foff = (unsigned)lane;
@@ -447,7 +455,12 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             // part 0: ramp-up steps 0..30 (captures compiled in; they are rare this early)
             const int e0 = s_star < 31 ? s_star : 31;
             const bool ramp_caps = fc_begin < e0 || bc_begin < e0;
-            if (one_table) {
+            if (no_addend) {
+                if (ramp_caps)
+                    PK_RUN(PK_CORE_FLANK0, true, true, e0);
+                else
+                    PK_RUN(PK_CORE_FLANK0, false, false, e0);
+            } else if (one_table) {
                 if (ramp_caps)
                     PK_RUN(PK_CORE_FLANK1R, true, true, e0);
                 else
@@ -466,7 +479,12 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 if (fc_begin > s && fc_begin < e) e = fc_begin;
                 if (bc_begin > s && bc_begin < e) e = bc_begin;
                 if (bc_end > s && bc_end < e) e = bc_end;
-                if (one_table) {
+                if (no_addend) {
+                    if (fc || bc)
+                        PK_RUN(PK_CORE_FLANK0, true, true, e);
+                    else
+                        PK_RUN(PK_CORE_FLANK0, false, false, e);
+                } else if (one_table) {
                     if (fc || bc)
                         PK_RUN(PK_CORE_FLANK1, true, true, e);
                     else
