@@ -212,6 +212,17 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
         for (int c = 0; c < 7; ++c) ctx->h_consts.cls_of[class_code[c]] = (unsigned char)c;
         ctx->h_consts.cls_of[STRK_PAD_FREE] = 7;
         ctx->h_consts.cls_of[STRK_PAD_PEN] = 7;
+        for (int k = 0; k <= STRK_SMAT_ROWS; ++k) {
+            const unsigned c = ctx->h_consts.cls_of[k];
+            unsigned w = 0x800u | 0x88u;  // not representable
+            if (!(c & 0x80)) {
+                const unsigned cls = c & 7u;
+                const unsigned add = cls < 4 || cls == 7 ? 0u : (unsigned)(ctx->h_consts.t8f[0] >> (8 * cls)) & 0xffu;
+                w = (cls < 4 ? cls : 8u) | ((cls < 4 ? 4u + cls : 8u) << 4) | (cls << 8) |
+                    ((cls < 4 || cls == 7) ? 0u : 0x1000u) | (add << 16);
+            }
+            ctx->h_consts.rowinfo[k] = w;
+        }
         ctx->h_consts.packed_ok = ok;
         int one = 1;  // one-table flank path: a non-ACGT row symbol must score the same against A, C, G and T
         for (int c = 4; c < 7; ++c)

@@ -67,7 +67,8 @@ __host__ __device__ inline size_t pk_scratch_words_per_warp(int R, int w_max) {
     return (size_t)(w_max + 1) * pk_quads(R) * 32 * 4;
 }
 // per-warp shared memory: [colT uint4 x colt_entries][prof u32 x prof_words][encoded db + motif bytes]
-__host__ __device__ inline size_t pk_code_bytes(int R) { return (size_t)(32 * R + 128 + 15) / 16 * 16; }
+// row symbols per register row, forward and backward (pad code on pad rows), then the motif
+__host__ __device__ inline size_t pk_code_bytes(int R) { return (size_t)(64 * R + 128 + 15) / 16 * 16; }
 __host__ __device__ inline size_t pk_smem16_per_warp(int R, const PackedDims &d) {
     return (size_t)d.colt_entries + ((size_t)d.prof_words * 4 + 15) / 16 + pk_code_bytes(R) / 16;
 }
@@ -240,14 +241,14 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     extern __shared__ uint4 smem_raw[];
     __shared__ SmemConsts sc;
     __shared__ unsigned long long t8f[STRK_NSYM_], t8b[STRK_NSYM_];
-    __shared__ unsigned char cls_of[STRK_SMAT_ROWS + 1];
+    __shared__ unsigned rowinfo[STRK_SMAT_ROWS + 1];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) sc.lut[k] = consts->lut[k];
     for (int k = threadIdx.x; k < STRK_SMAT_ROWS * STRK_NSYM_; k += blockDim.x) sc.smat[k] = consts->smat[k];
     for (int k = threadIdx.x; k < STRK_NSYM_; k += blockDim.x) {
         t8f[k] = consts->t8f[k];
         t8b[k] = consts->t8b[k];
     }
-    for (int k = threadIdx.x; k < STRK_SMAT_ROWS; k += blockDim.x) cls_of[k] = consts->cls_of[k];
+    for (int k = threadIdx.x; k <= STRK_SMAT_ROWS; k += blockDim.x) rowinfo[k] = consts->rowinfo[k];
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -267,13 +268,15 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
     uint4 *colT = smem_raw + (size_t)warp * pk_smem16_per_warp(R, dims);  // entry [j + 31], columns -31 .. Lmax + 31
     unsigned *prof = (unsigned *)(colT + dims.colt_entries);
-    unsigned char *codes = (unsigned char *)(prof + (dims.prof_words + 3) / 4 * 4);  // encoded db, then motif
-    unsigned char *mcodes = codes + 32 * R;
+    // symbol codes by REGISTER row (row I of the padded strip, 0-based): rowF[I] = db[I - off], rowB[I] = db[N - 1 - I]
+    // (the backward sweep's row), pad code on the pad rows; each lane reads its R consecutive bytes of both
+    unsigned char *rowF = (unsigned char *)(prof + (dims.prof_words + 3) / 4 * 4);
+    unsigned char *rowB = rowF + N;
+    unsigned char *mcodes = rowB + N;
     uint4 *scr = scratch + (size_t)warp_global * (size_t)(dims.w_max + 1) * QN * 32;
     const unsigned tinc = (s2_beg ? (unsigned)g : 0u) | ((s2_end ? (unsigned)g : 0u) << 16);
     const unsigned ginc = (unsigned)g | ((unsigned)g << 16);
     const int g2 = 2 * g;
-    const int padF = STRK_PAD_PEN, padB = STRK_PAD_PEN;  // biased score 0 in every mode: pad rows copy (see borders)
 
     for (int fam_idx = warp_global; fam_idx < n_list; fam_idx += total_warps) {
         const int fam_id = list[fam_idx];
@@ -306,7 +309,12 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
         // ---- stage the encoded read and motif in shared memory (one coalesced pass over the arena bytes)
         bool motif_acgt = true;
-        for (int i = lane; i < n1; i += 32) codes[i] = sc.lut[db[i]];
+        for (int d = lane; d < n1; d += 32) {
+            const unsigned char c = sc.lut[db[d]];
+            rowF[d + off] = c;
+            rowB[N - 1 - d] = c;
+        }
+        for (int I = lane; I < off; I += 32) rowF[I] = rowB[I] = (unsigned char)STRK_PAD_PEN;
         for (int k = lane; k < m; k += 32) {
             const unsigned char c = sc.lut[motif[k]];
             mcodes[k] = c;
@@ -327,8 +335,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             const int j = e - 31;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (j >= 1) {
-                const int sf = j <= f.n_fl ? codes[j - 1] : mcodes[mod_m(j - f.n_fl - 1)];
-                const int sb = j <= f.n_fr ? codes[n1 - j] : mcodes[m - 1 - mod_m(j - f.n_fr - 1)];
+                const int sf = j <= f.n_fl ? rowF[off + j - 1] : mcodes[mod_m(j - f.n_fl - 1)];
+                const int sb = j <= f.n_fr ? rowF[N - j] : mcodes[m - 1 - mod_m(j - f.n_fr - 1)];
                 acgt = acgt && sf < 4 && sb < 4;
                 const unsigned long long a = t8f[sf], b = t8b[sb];
                 v = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
@@ -337,31 +345,22 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         const bool cols_acgt = __all_sync(0xffffffffu, acgt);
 
-        // ---- row symbols -> PRMT selectors (one-table format first: the profile build uses it too)
+        // ---- row symbols -> PRMT selectors (one-table format first: the profile build uses it too).  One look-up
+        // per row and direction: rowinfo[code] holds the selector nibbles, the class, the addend and the flags.
         PkState<R> st;
-        unsigned cls[R];  // forward class | backward class << 4 | forward code << 8 | backward code << 16
-        bool rows_ok = true, rows_plain = true;  // plain = A/C/G/T or pad: nothing column-dependent rides in selB
+        const unsigned char *myF = rowF + lane * R, *myB = rowB + lane * R;
+        unsigned flags_or = 0u;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = lane * R + r + 1 - off;  // real row (1..n1), <= 0: pad
-            int cf = padF, cb = padB;
-            if (i >= 1) {
-                cf = codes[i - 1];
-                cb = codes[n1 - i];
-            }
-            unsigned kf = cls_of[cf], kb = cls_of[cb];
-            if ((kf | kb) & 0x80) rows_ok = false;
-            kf &= 7;
-            kb &= 7;
-            rows_plain = rows_plain && (kf < 4 || kf == 7) && (kb < 4 || kb == 7);
-            cls[r] = kf | (kb << 4) | ((unsigned)cf << 8) | ((unsigned)cb << 16);
+            const unsigned wf = rowinfo[myF[r]], wb = rowinfo[myB[r]];
+            flags_or |= wf | wb;
             // bytes 0-3 of the pair {forward table, backward table} = forward classes, 4-7 = backward classes;
             // selector nibble 8 = sign-replicate of byte 0 = 0x00
-            st.selA[r] = (kf < 4 ? kf : 8u) | 0x0080u | ((kb < 4 ? 4u + kb : 8u) << 8) | 0x8000u;
-            const unsigned af = kf < 4 ? 0u : (unsigned)(t8f[0] >> (8 * kf)) & 0xffu;
-            const unsigned ab = kb < 4 ? 0u : (unsigned)(t8b[0] >> (8 * kb)) & 0xffu;
-            st.selB[r] = af | (ab << 16);
+            st.selA[r] = (wf & 0xfu) | ((wb & 0xf0u) << 4) | 0x8080u;
+            st.selB[r] = ((wf >> 16) & 0xffu) | (wb & 0xff0000u);
         }
+        const bool rows_ok = !(flags_or & 0x800u);
+        const bool rows_plain = !(flags_or & 0x1000u);  // A/C/G/T or pad only: no row carries an addend
         if (!__all_sync(0xffffffffu, rows_ok)) {  // IUPAC code inside the read
             if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
             continue;
@@ -386,8 +385,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 const int sb = mcodes[m - 1 - mod_m(k + Lmax - f.n_fr)];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int vf = sc.smat[((cls[r] >> 8) & 0xff) * STRK_NSYM_ + sf] + g2;
-                    const int vb = sc.smat[((cls[r] >> 16) & 0xff) * STRK_NSYM_ + sb] + g2;
+                    const int vf = sc.smat[myF[r] * STRK_NSYM_ + sf] + g2;
+                    const int vb = sc.smat[myB[r] * STRK_NSYM_ + sb] + g2;
                     prof[((k * RH + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = (unsigned)vf | ((unsigned)vb << 16);
                 }
             }
@@ -395,8 +394,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         if (!one_table) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                st.selA[r] = (cls[r] & 7u) | 0x8880u;
-                st.selB[r] = (((cls[r] >> 4) & 7u) << 8) | 0x8088u;
+                st.selA[r] = ((rowinfo[myF[r]] >> 8) & 7u) | 0x8880u;
+                st.selB[r] = (((rowinfo[myB[r]] >> 8) & 7u) << 8) | 0x8088u;
             }
         }
 

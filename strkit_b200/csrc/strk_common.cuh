@@ -29,6 +29,11 @@ struct ScoreConsts {
     // the forward (t8f) and backward (t8b) sweeps differ in the pad-row byte only
     unsigned long long t8f[STRK_NSYM_], t8b[STRK_NSYM_];
     unsigned char cls_of[STRK_SMAT_ROWS + 1];  // symbol code -> PRMT row class, 0x80 = not representable
+    // packed kernel, per row-symbol code: everything the selector build needs in one word
+    //   [3:0]  forward selector nibble (class 0-3, or 8 = PRMT zero byte)   [7:4] backward nibble (4 + class, or 8)
+    //   [10:8] row class 0-7 (two-table path)   [11] not representable   [12] carries an addend (N / X / other)
+    //   [23:16] the addend: biased score of the class against A/C/G/T (one-table path)
+    unsigned rowinfo[STRK_SMAT_ROWS + 1];
     int packed_ok;                             // every biased score fits a positive byte
     int one_table_ok;                          // N / X / other rows score the same against A, C, G and T
     // = 1 in every entry, opaque to the compiler: multiplier of the FMA-pipe adds (IMAD d, one, s).  Read as a
