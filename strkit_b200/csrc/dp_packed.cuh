@@ -523,56 +523,63 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         // ---- combine: score(n) for every candidate of the window
         __syncwarp();
         const unsigned *scw = (const unsigned *)scr;
-        const int bslot = nW;
+        const unsigned bbase = (unsigned)nW * (QN * 128);  // word offset of the backward slot
         unsigned Bv[R];  // backward value paired with each forward row (low half), 0 for pad rows
+        {
+            // forward row If = lane * R + r + 1 pairs with backward row Ib = N + off - If: consecutive, descending,
+            // so its (lane, register) position is stepped instead of divided out per row
+            int ib1 = N + off - (lane * R + 1) - 1;  // Ib - 1 for r = 0
+            int lb = ib1 / R, rb = ib1 - lb * R;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int If = lane * R + r + 1;
-            unsigned v = 0u;
-            if (If >= off) {
-                const int Ib = N + off - If;  // in [off, N]
-                const int lb = (Ib - 1) / R, rb = (Ib - 1) % R;
-                v = scw[(((size_t)bslot * QN + (rb >> 2)) * 32 + lb) * 4 + (rb & 3)] >> 16;
+            for (int r = 0; r < R; ++r) {
+                unsigned v = 0u;
+                if (lane * R + r + 1 >= off) v = scw[bbase + (unsigned)(((rb >> 2) * 32 + lb) * 4 + (rb & 3))] >> 16;
+                Bv[r] = v;
+                if (--rb < 0) rb = R - 1, --lb;
             }
-            Bv[r] = v;
         }
-        const int bextra = (int)(scw[(((size_t)bslot * QN + (R >> 2)) * 32 + 31) * 4 + (R & 3)] >> 16);
-        int *out = table + f.out_off;
+        const int bextra = (int)(scw[bbase + (unsigned)(((R >> 2) * 32 + 31) * 4 + (R & 3))] >> 16);
         constexpr int WB = 4;  // candidates per batch of loads (hides the L2 round trip)
-        for (int w0 = 0; w0 < nW; w0 += WB) {
-            uint4 q4[WB][QN];
+        for (int g0 = 0; g0 < nW; g0 += 32) {  // 32 candidates at a time: lane w keeps the reduced values of g0 + w
+            const int gend = g0 + 32 < nW ? g0 + 32 : nW;
+            unsigned my_v = 0u, my_flast = 0u;
+            for (int w0 = g0; w0 < gend; w0 += WB) {
+                uint4 q4[WB][QN];
 #pragma unroll
-            for (int b = 0; b < WB; ++b) {
-                const int ww = w0 + b < nW ? w0 + b : nW - 1;
+                for (int b = 0; b < WB; ++b) {
+                    const int ww = w0 + b < gend ? w0 + b : gend - 1;
 #pragma unroll
-                for (int q = 0; q < QN; ++q) q4[b][q] = scr[((size_t)ww * QN + q) * 32 + lane];
-            }
-#pragma unroll
-            for (int b = 0; b < WB; ++b) {
-                const int ww = w0 + b;
-                unsigned acc = 0u;
-#pragma unroll
-                for (int q = 0; q < QN; ++q) {
-                    const uint4 v = q4[b][q];
-                    if (4 * q + 0 < R) acc = __viaddmax_u16x2(v.x, Bv[(4 * q + 0) % R], acc);
-                    if (4 * q + 1 < R) acc = __viaddmax_u16x2(v.y, Bv[(4 * q + 1) % R], acc);
-                    if (4 * q + 2 < R) acc = __viaddmax_u16x2(v.z, Bv[(4 * q + 2) % R], acc);
-                    if (4 * q + 3 < R) acc = __viaddmax_u16x2(v.w, Bv[(4 * q + 3) % R], acc);
+                    for (int q = 0; q < QN; ++q) q4[b][q] = scr[(unsigned)((ww * QN + q) * 32 + lane)];
                 }
-                const unsigned v = __reduce_max_sync(0xffffffffu, acc & 0xffffu);
-                // lane 31's prefix-max word of this candidate column (forward half)
-                const unsigned pmw = (&q4[b][R >> 2].x)[R & 3];
-                const unsigned flast = __shfl_sync(0xffffffffu, pmw, 31) & 0xffffu;
-                if (lane0 && ww < nW) {
-                    const int p = f.n_fl + m * (a_lo + ww);
-                    int best = (int)v - g * (N + off + p + colsB);
-                    if (s2_end) best = max(best, (int)flast - g * (N + p));
-                    if (s2_beg) {
-                        const int border = s1_end ? -g : -g * n1;  // backward cell (n1, 0)
-                        best = max(best, max(bextra - g * (N + colsB), border));
+#pragma unroll
+                for (int b = 0; b < WB; ++b) {
+                    const int ww = w0 + b;
+                    if (ww >= gend) break;  // warp-uniform
+                    unsigned acc = 0u;
+#pragma unroll
+                    for (int q = 0; q < QN; ++q) {
+                        const uint4 v = q4[b][q];
+                        if (4 * q + 0 < R) acc = __viaddmax_u16x2(v.x, Bv[(4 * q + 0) % R], acc);
+                        if (4 * q + 1 < R) acc = __viaddmax_u16x2(v.y, Bv[(4 * q + 1) % R], acc);
+                        if (4 * q + 2 < R) acc = __viaddmax_u16x2(v.z, Bv[(4 * q + 2) % R], acc);
+                        if (4 * q + 3 < R) acc = __viaddmax_u16x2(v.w, Bv[(4 * q + 3) % R], acc);
                     }
-                    out[ww] = best;
+                    const unsigned v = __reduce_max_sync(0xffffffffu, acc & 0xffffu);
+                    // lane 31's prefix-max word of this candidate column (forward half)
+                    const unsigned pmw = (&q4[b][R >> 2].x)[R & 3];
+                    const unsigned flast = __shfl_sync(0xffffffffu, pmw, 31) & 0xffffu;
+                    if (lane == ww - g0) my_v = v, my_flast = flast;
                 }
+            }
+            if (g0 + lane < gend) {  // un-bias and close the free-end cases: one candidate per lane, coalesced store
+                const int p = f.n_fl + m * (a_lo + g0 + lane);
+                int best = (int)my_v - g * (N + off + p + colsB);
+                if (s2_end) best = max(best, (int)my_flast - g * (N + p));
+                if (s2_beg) {
+                    const int border = s1_end ? -g : -g * n1;  // backward cell (n1, 0)
+                    best = max(best, max(bextra - g * (N + colsB), border));
+                }
+                table[f.out_off + g0 + lane] = best;
             }
         }
         __syncwarp();
