@@ -84,7 +84,7 @@ struct strk_ctx {
     DevBuf<FamDesc> fams;
     DevBuf<int> table;
     DevBuf<long long> table64;
-    DevBuf<int> list_a, list_b;      // widening-pass lists
+    DevBuf<int> list_a, list_b, list_d;  // widening-pass lists
     DevBuf<long long> list_c;
     DevBuf<int> fallback;            // reads the packed kernel handed to the general kernel
     DevBuf<uint4> pk_scratch;        // captured DP columns of the packed kernel (per resident warp)
@@ -257,6 +257,7 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     ctx->table64.release();
     ctx->list_a.release();
     ctx->list_b.release();
+    ctx->list_d.release();
     ctx->list_c.release();
     ctx->fallback.release();
     ctx->pk_scratch.release();
@@ -597,7 +598,8 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
     const long long *d_slot_begin = nullptr;
     std::vector<int> h_read_ids, h_locus_ids;
     std::vector<long long> h_slot_begin;
-    std::vector<unsigned char> h_status;
+    std::vector<unsigned char> h_status, h_bin;
+    std::vector<int> h_class_lists;
     float ms_dp = 0.f, ms_replay = 0.f;
 
     for (int pass = 0;; ++pass) {
@@ -617,23 +619,55 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[0], st));
         int rc = STRK_OK;
-        const bool use_packed = pass == 0 && kernel != STRK_KERNEL_GENERAL && ctx->h_consts.packed_ok;
+        // packed kernel: every pass whose window it can hold (the first widening pass included: 8x the first window)
+        const bool use_packed = kernel != STRK_KERNEL_GENERAL && ctx->h_consts.packed_ok && W <= PK_WINDOW_MAX;
         long long n_packed = 0;
         if (!use_packed) {
             rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots, b->d_arena, ctx->table.p,
                                 b_len, rowlen, st);
             if (rc) return rc;
         } else {
-            // pass 0: slot == read.  Packed kernel per R segment; what it cannot take goes to the general kernel.
+            // Packed kernel per rows-per-lane class; what it cannot take goes to the general kernel.
+            // Pass 0: slot == read, the class segments of the batch's work order.  Widening passes: the slots of
+            // the loci being redone, binned on the host by the class planned for their reads at upload time.
             if (ctx->fallback.reserve((size_t)b->n_reads) != cudaSuccess) {
                 cudaGetLastError();
                 return set_err(STRK_ERR_NOMEM, "cannot allocate the fallback list");
+            }
+            const int *seg_list[STRK_PK_NBIN];
+            long long seg_cnt[STRK_PK_NBIN];
+            if (pass == 0) {
+                for (int k = 0; k < STRK_PK_NBIN; ++k) seg_list[k] = b->d_order + b->bin_off[k], seg_cnt[k] = b->bin_cnt[k];
+                seg_cnt[0] = b->n_general;
+                seg_list[0] = b->d_order;
+            } else {
+                if (h_bin.empty()) {
+                    h_bin.resize((size_t)b->n_reads);
+                    CU(cudaMemcpyAsync(h_bin.data(), b->bin.p, (size_t)b->n_reads, cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                }
+                std::vector<int> by_class[STRK_PK_NBIN];
+                for (size_t sl = 0; sl < h_read_ids.size(); ++sl) by_class[h_bin[(size_t)h_read_ids[sl]]].push_back((int)sl);
+                h_class_lists.clear();
+                size_t at[STRK_PK_NBIN];
+                for (int k = 0; k < STRK_PK_NBIN; ++k) {
+                    at[k] = h_class_lists.size();
+                    h_class_lists.insert(h_class_lists.end(), by_class[k].begin(), by_class[k].end());
+                }
+                if (ctx->list_d.reserve(h_class_lists.size()) != cudaSuccess) {
+                    cudaGetLastError();
+                    return set_err(STRK_ERR_NOMEM, "cannot allocate widening lists");
+                }
+                CU(cudaMemcpyAsync(ctx->list_d.p, h_class_lists.data(), h_class_lists.size() * sizeof(int),
+                                   cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));  // h_class_lists is reused by the next pass
+                for (int k = 0; k < STRK_PK_NBIN; ++k) seg_list[k] = ctx->list_d.p + at[k], seg_cnt[k] = (long long)by_class[k].size();
             }
             CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
             // one launch per rows-per-lane class, back to back on the run's stream (spreading the classes over
             // several streams was measured slower: concurrent grids with different footprints fragment the SMs)
             for (int k = STRK_PK_RMAX; k >= 1; --k) {
-                if (!b->bin_cnt[k]) continue;
+                if (!seg_cnt[k]) continue;
                 const int R = k;
                 PackedDims dims;
                 dims.colt_entries = b->bin_flank[k] + 64;
@@ -641,17 +675,16 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                 dims.w_max = (W + 3) / 4 * 4;
                 if (pk_smem_bytes(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
-                    rc = launch_general(ctx, false, ctx->fams.p, b->d_order + b->bin_off[k], b->bin_cnt[k], b->d_arena,
-                                        ctx->table.p, b_len, rowlen, st);
+                    rc = launch_general(ctx, false, ctx->fams.p, seg_list[k], seg_cnt[k], b->d_arena, ctx->table.p, b_len,
+                                        rowlen, st);
                     if (rc) return rc;
                     continue;
                 }
-                rc = launch_packed(ctx, R, ctx->fams.p, b->d_order + b->bin_off[k], (int)b->bin_cnt[k], b->d_arena,
-                                   ctx->table.p, dims, st);
+                rc = launch_packed(ctx, R, ctx->fams.p, seg_list[k], (int)seg_cnt[k], b->d_arena, ctx->table.p, dims, st);
                 if (rc) return rc;
-                n_packed += b->bin_cnt[k];
+                n_packed += seg_cnt[k];
             }
-            rc = launch_general(ctx, false, ctx->fams.p, b->d_order, b->n_general, b->d_arena, ctx->table.p, b_len, rowlen, st);
+            rc = launch_general(ctx, false, ctx->fams.p, seg_list[0], seg_cnt[0], b->d_arena, ctx->table.p, b_len, rowlen, st);
             if (rc) return rc;
             if (n_packed) {
                 rc = launch_general(ctx, false, ctx->fams.p, ctx->fallback.p, n_packed, b->d_arena, ctx->table.p, b_len,

@@ -39,6 +39,7 @@
 #include "strk_common.cuh"
 
 #define PK_FLANK_MAX 160  // longest flank the packed kernel stages (reference default flank_size = 70)
+#define PK_WINDOW_MAX 128  // widest window (candidate sizes per read) a batch pass gives to the packed kernel
 #ifndef PK_WARPS
 #define PK_WARPS 4  // warps (= reads in flight) per CTA
 #endif
