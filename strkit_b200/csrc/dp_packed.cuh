@@ -116,23 +116,39 @@ struct PkState {
     unsigned foff;  // next forward capture slot: uint4 index into the warp's scratch (lane offset applied)
 };
 
-// One column of the wavefront -> scratch: H[0..R) and the prefix-max word, as QN 128-bit stores.  The words after
-// the prefix maximum are never read; they are filled with DISTINCT live registers so that ptxas can keep the last
-// quad in place (a duplicated register would force copies before the vector store).
+// One column of the wavefront -> scratch: H[0..R) then the prefix-max word, word w of the column at
+// dst[(w / 4) * 32].{x,y,z,w}.  Full quads go out as predicated 128-bit stores; the tail (R % 4 cells and the
+// prefix maximum) as 64- / 32-bit pieces, so that no register has to be copied into an aligned quad first.
+__device__ __forceinline__ void pk_st4(unsigned *p, unsigned a, unsigned b, unsigned c, unsigned d, unsigned on) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"l"(p), "r"(a),
+                 "r"(b), "r"(c), "r"(d), "r"(on)
+                 : "memory");
+}
+__device__ __forceinline__ void pk_st2(unsigned *p, unsigned a, unsigned b, unsigned on) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.global.v2.u32 [%0], {%1, %2}; }" ::"l"(p), "r"(a), "r"(b), "r"(on)
+                 : "memory");
+}
+__device__ __forceinline__ void pk_st1(unsigned *p, unsigned a, unsigned on) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.global.u32 [%0], %1; }" ::"l"(p), "r"(a), "r"(on) : "memory");
+}
+
 template <int R>
 __device__ __forceinline__ void pk_capture(const PkState<R> &st, uint4 *__restrict__ dst, const unsigned on) {
-    constexpr int QN = (R + 1 + 3) / 4;
-    const unsigned fill[4] = {st.pm, st.prev_up, st.topv, st.foff};
+    constexpr int QF = R / 4, REM = R % 4;  // full quads, cells in the partial one
 #pragma unroll
-    for (int q = 0; q < QN; ++q) {
-        uint4 v;
-        v.x = 4 * q + 0 < R ? st.H[(4 * q + 0) % R] : fill[(4 * q + 0 - R) & 3];
-        v.y = 4 * q + 1 < R ? st.H[(4 * q + 1) % R] : fill[(4 * q + 1 - R) & 3];
-        v.z = 4 * q + 2 < R ? st.H[(4 * q + 2) % R] : fill[(4 * q + 2 - R) & 3];
-        v.w = 4 * q + 3 < R ? st.H[(4 * q + 3) % R] : fill[(4 * q + 3 - R) & 3];
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"l"(dst + q * 32),
-                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(on)
-                     : "memory");
+    for (int q = 0; q < QF; ++q)
+        pk_st4((unsigned *)(dst + q * 32), st.H[4 * q], st.H[4 * q + 1], st.H[4 * q + 2], st.H[4 * q + 3], on);
+    unsigned *tail = (unsigned *)(dst + QF * 32);
+    if (REM == 1) {
+        pk_st2(tail, st.H[R - 1], st.pm, on);
+    } else if (REM == 2) {
+        pk_st2(tail, st.H[R - 2], st.H[R - 1], on);
+        pk_st1(tail + 2, st.pm, on);
+    } else if (REM == 3) {
+        pk_st2(tail, st.H[R - 3], st.H[R - 2], on);
+        pk_st2(tail + 2, st.H[R - 1], st.pm, on);
+    } else {
+        pk_st1(tail, st.pm, on);
     }
 }
 
