@@ -11,22 +11,24 @@
 //
 // Cell update in 2 integer instructions.  With H' = H + g*(row + col) the linear-gap recurrence
 //     H = max(diag + s, max(up, left) - g)      becomes      H' = max3(diag' + (s + 2g), up', left')
-// i.e. one add (IADD3 / IMAD.IADD) and one VIMNMX3.U16x2; every H' is >= 0, so unsigned 16-bit lanes never
-// underflow and a plain 32-bit add cannot carry between the halves.
+// i.e. one add (an IMAD, so that it issues on the FMA pipe) and one VIMNMX3.U16x2 written in place; every H' is
+// >= 0, so unsigned 16-bit lanes never underflow and a plain 32-bit add cannot carry between the halves.
 //
 // Substitution scores without a per-cell table walk:
 //   * flank phase (columns still inside fl / fr): PRMT as an 8-entry byte LUT.  The 8-byte table comes
-//     from the column symbol (one LDS.128 per step), the selector from the row symbol (fixed register),
-//     the upper byte of each half is produced by PRMT's sign-replicate mode.  2 PRMT + IADD3 + VIMNMX3.
+//     from the column symbol (one shared-memory load per step), the selector from the row symbol (fixed
+//     register), the upper byte of each half is produced by PRMT's sign-replicate mode.  Per cell pair:
+//     PRMT + IMAD + VIMNMX3 for a read whose rows are all A/C/G/T (FLANK0), one more IMAD when rows hold X / N
+//     wildcards (FLANK1: their score rides along as a per-row addend), two PRMT otherwise (FLANK2).
 //   * motif phase (both halves inside the periodic tract): the pair of column symbols repeats with
-//     period m, so a packed query profile prof[k][row] is built once per read in shared memory and the
-//     step costs LDS + IADD + VIMNMX3 per cell pair.  The candidate is never materialised.
+//     period m, so a packed query profile is built once per read in shared memory (stored as row pairs) and
+//     the step costs LDS.64 / 2 + IMAD.IADD + VIMNMX3 per cell pair.  The candidate is never materialised.
 //
 // The step loops are branch-free.  Lanes that have not started yet (column <= 0) run on an all-zero score
 // table, which leaves their border column untouched (the biased borders are non-decreasing down the rows);
 // lanes that are past the last column compute values nobody reads.  Candidate columns (and the final column
-// of the backward half) are captured with predicated 128-bit stores into a per-warp scratch that stays in
-// L2; the combine pass reads them back.
+// of the backward half) are captured with predicated stores into a per-warp scratch that mostly stays in
+// L2; the combine pass reads them back (one candidate per lane for the closing arithmetic).
 //
 // Rows are front-padded to 32*R (> n1, so there is always at least one pad row, which doubles as DP row 0);
 // row n1 is therefore always the last register of lane 31.  Pad rows score zero and so copy the row above them;
