@@ -296,3 +296,98 @@ def test_ref_counts_batch_with_reference_tiers(sb, oracle):
         (cn, score), lo, ro, (n_off, n_fin), (fl2, tr2, fr2) = oracle.get_ref_repeat_count(
             starts[i], tr, fl, fr, motif, ref_sizes[i], 5, rcs[i][0], rcs[i][1], rcs[i][2])
         assert got[i].tolist() == [cn, score, lo, ro, n_off, n_fin, len(fl2), len(fr2)], (i, fams[i][0], rcs[i])
+
+
+def test_ragged_loci_zero_one_and_max_reads(sb, oracle):
+    """Loci with 0, 1, 3 and 250 reads (the reference caps a locus at max_reads = 250, params.py:21) in one batch;
+    the carried start offset of call_locus.py:1129-1161 runs over every read of the 250-read locus."""
+    from strkit_b200.batcher import LocusReads, pack_loci
+    from tests.helpers import mutate, rand_seq
+
+    rng = np.random.default_rng(21)
+    loci = []
+    for n_reads in (0, 1, 250, 3, 0, 17):
+        m = int(rng.integers(2, 7))
+        motif = rand_seq(rng, m)
+        k = int(rng.integers(8, 30))
+        fl, fr = rand_seq(rng, 70), rand_seq(rng, 70)
+        trs, fls, frs, est = [], [], [], []
+        for _ in range(n_reads):
+            kk = k + int(rng.choice([-2, -1, 0, 0, 0, 1, 2]))
+            tr = mutate(rng, motif * kk, 0.01, 0.01, 0.01)
+            trs.append(tr or motif)
+            fls.append(mutate(rng, fl, 0.01, 0.0, 0.0)[-70:] or "A")
+            frs.append(mutate(rng, fr, 0.01, 0.0, 0.0)[:70] or "A")
+            est.append(round(len(trs[-1]) / m))
+        loci.append(LocusReads(motif, est, trs, fls, frs))
+    batch = pack_loci(loci)
+    assert np.diff(batch.read_begin).tolist() == [0, 1, 250, 3, 0, 17]
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    got = eng.count_reads(batch, params)
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin, batch.motif_off,
+                                batch.motif_len, n_threads=8)
+    assert np.array_equal(got, want), np.flatnonzero((got != want).any(axis=1))[:10]
+    eng.close()
+
+
+def test_full_size_catalog_properties(sb, oracle):
+    """BASELINE config 2 at its full size: 1 048 576 loci x 30 reads (31.5 M reads), streamed as 32 768-locus
+    blocks.  Size-independent checks: (i) bit-exact parity with the CPU oracle on loci sampled from blocks spread over
+    the whole catalog; (ii) results do not depend on how the catalog is cut into blocks; (iii) invariants of every
+    read: score <= 2 * |db| (match = 2), 1 <= n_explored <= max_iters + 2 * range + 1, the reported start within the
+    carried-offset range of its estimate; (iv) the count equals the number of copies written into the read for the
+    overwhelming majority of (HiFi-like) reads."""
+    import torch
+
+    from strkit_b200 import synth
+
+    n_blocks, block = 32, 32768
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    rng = np.random.default_rng(4)
+    check_blocks = set(rng.choice(n_blocks, size=6, replace=False).tolist())
+
+    def blocks():
+        for i in range(n_blocks):
+            sbatch = synth.generate(synth.CONFIGS[2], block, seed=910_000 + i, device="cuda", chunk_loci=4096)
+            hb = sbatch.to_host(pin=True)
+            hb.true_cn = sbatch.true_cn.cpu().numpy()
+            del sbatch
+            yield hb
+
+    kept = {}
+    n_reads = n_equal = 0
+
+    def tee():
+        for i, hb in enumerate(blocks()):
+            stash.append((i, hb))
+            yield hb
+
+    stash: list = []
+    for out in eng.count_reads_stream(tee(), params):
+        i, hb = stash.pop(0)
+        db_len = hb.lens.sum(axis=1)
+        assert (out[:, 1] <= 2 * db_len).all() and (out[:, 0] >= 0).all()
+        assert (out[:, 2] >= 1).all() and (out[:, 2] <= 50 + 2 * 3 + 1).all()
+        assert (np.abs(out[:, 3] - hb.est_cn) <= 64).all()
+        n_reads += out.shape[0]
+        n_equal += int((out[:, 0] == hb.true_cn).sum())
+        if i in check_blocks:
+            kept[i] = (hb, out.copy())
+    assert n_reads == n_blocks * block * 30
+    assert n_equal / n_reads > 0.97
+    torch.cuda.empty_cache()
+    for i, (hb, out) in sorted(kept.items()):
+        lo = int(rng.integers(0, block - 96))
+        sub = hb.slice_loci(lo, lo + 96)
+        want, _ = oracle.count_loci(sub.arena, sub.seq_off, sub.lens, sub.est_cn, sub.read_begin, sub.motif_off,
+                                    sub.motif_len, n_threads=8)
+        r0, r1 = int(hb.read_begin[lo]), int(hb.read_begin[lo + 96])
+        assert np.array_equal(out[r0:r1], want), (i, lo)
+        # a different cut of the same loci gives the same rows
+        cut = int(rng.integers(1, block - 1))
+        a, b = hb.slice_loci(0, cut), hb.slice_loci(cut, block)
+        again = np.concatenate(list(eng.count_reads_stream([a, b], params)))
+        assert np.array_equal(again, out), (i, cut)
+    eng.close()
