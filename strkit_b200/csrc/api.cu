@@ -1,5 +1,6 @@
 // api.cu -- C ABI (include/strkit_b200.h), context and batch management, launch orchestration.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -14,6 +15,7 @@
 #include "plan.cuh"
 #include "int_peak.cuh"
 #include "replay.cuh"
+#include "ref_path.cuh"
 #include "strk_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -90,6 +92,11 @@ struct strk_ctx {
     DevBuf<uint4> pk_scratch;        // captured DP columns of the packed kernel (per resident warp)
     DevBuf<double> al_rep[3];        // allele calling: replicate means / weights / stdevs of one chunk of loci
     DevBuf<unsigned char> al_peaks;  //                 replicate peak counts
+    // reference path (strk_ref_counts): per-locus arrays, pending lists, and the one-read-per-locus batch of phase 2
+    DevBuf<unsigned char> ref_arena;
+    DevBuf<unsigned long long> ref_u64[2];
+    DevBuf<int> ref_i[12];
+    struct strk_batch *ref_batch = nullptr;
     DevBuf<int> al_i[8];             //                 per-read / per-locus integer arrays (recycled across calls)
     DevBuf<double> al_d[3];
     DevBuf<long long> al_rb;
@@ -251,6 +258,11 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->reuse) strk_batch_free(ctx, ctx->reuse);
     ctx->reuse = nullptr;
+    if (ctx->ref_batch) strk_batch_free(ctx, ctx->ref_batch);
+    ctx->ref_batch = nullptr;
+    ctx->ref_arena.release();
+    for (int k = 0; k < 2; ++k) ctx->ref_u64[k].release();
+    for (int k = 0; k < 12; ++k) ctx->ref_i[k].release();
     ctx->scratch.release();
     ctx->fams.release();
     ctx->table.release();
@@ -429,51 +441,10 @@ extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b) {
     return STRK_OK;
 }
 
-// H2D into (possibly recycled) device buffers, then validation + work planning on the device (plan.cuh)
-static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
-                      const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
-                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci) {
-    if (n_reads < 0 || n_loci < 0 || n_reads > 0x7ffffff0LL || n_loci > 0x7ffffff0LL)
-        return set_err(STRK_ERR_ARG, "batch: bad counts (%lld reads, %lld loci)", (long long)n_reads, (long long)n_loci);
-    if ((n_reads && (!arena || !seq_off || !lens || !est_cn)) || !read_begin || (n_loci && (!motif_off || !motif_len)))
-        return set_err(STRK_ERR_ARG, "batch: null array");
-    if (read_begin[0] != 0 || read_begin[n_loci] != n_reads)
-        return set_err(STRK_ERR_ARG, "batch: read_begin must run from 0 to n_reads");
-    CU(cudaSetDevice(ctx->device));
-    b->n_reads = n_reads;
-    b->n_loci = n_loci;
-    b->h_read_begin.assign(read_begin, read_begin + n_loci + 1);
-    b->n_general = 0;
-    for (int k = 0; k < STRK_PK_NBIN; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
-    b->max_n1 = b->mb_cols_base = b->mb_m = 0;
-
+// Validation + work planning of a batch whose arrays are already on the device (b->d_*, n_reads, n_loci set).
+static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
+    const long long n_reads = b->n_reads, n_loci = b->n_loci;
     cudaStream_t st = ctx->stream;
-    cudaError_t e = cudaSuccess;
-#define UP(buf, dst, src, n) \
-    if (e == cudaSuccess) e = upload(b->buf, &b->dst, src, (size_t)(n), st)
-    UP(arena, d_arena, (const unsigned char *)arena, arena_bytes);
-    UP(seq_off, d_seq_off, (const unsigned long long *)seq_off, n_reads);
-    UP(lens, d_lens, (const int *)lens, 3 * n_reads);
-    UP(est, d_est, (const int *)est_cn, n_reads);
-    UP(read_begin, d_read_begin, (const long long *)read_begin, n_loci + 1);
-    UP(motif_off, d_motif_off, (const unsigned long long *)motif_off, n_loci);
-    UP(motif_len, d_motif_len, (const int *)motif_len, n_loci);
-#undef UP
-    const size_t nr = (size_t)(n_reads ? n_reads : 1);
-    if (e == cudaSuccess) e = b->read_locus.reserve(nr);
-    if (e == cudaSuccess) e = b->order.reserve(nr);
-    if (e == cudaSuccess) e = b->bin.reserve(nr);
-    if (e == cudaSuccess) e = b->out.reserve(nr * 4);
-    if (e == cudaSuccess) e = b->status.reserve((size_t)(n_loci ? n_loci : 1));
-    b->d_read_locus = b->read_locus.p;
-    b->d_order = b->order.p;
-    b->d_out = b->out.p;
-    b->d_status = b->status.p;
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "batch upload: %s",
-                       cudaGetErrorString(e));
-    }
     if (n_reads == 0) {
         CU(cudaStreamSynchronize(st));
         return STRK_OK;
@@ -529,6 +500,54 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));  // `off` is on this stack frame; the caller's buffers may go away after return
     return STRK_OK;
+}
+
+// H2D into (possibly recycled) device buffers, then validation + work planning on the device (plan.cuh)
+static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                      const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci) {
+    if (n_reads < 0 || n_loci < 0 || n_reads > 0x7ffffff0LL || n_loci > 0x7ffffff0LL)
+        return set_err(STRK_ERR_ARG, "batch: bad counts (%lld reads, %lld loci)", (long long)n_reads, (long long)n_loci);
+    if ((n_reads && (!arena || !seq_off || !lens || !est_cn)) || !read_begin || (n_loci && (!motif_off || !motif_len)))
+        return set_err(STRK_ERR_ARG, "batch: null array");
+    if (read_begin[0] != 0 || read_begin[n_loci] != n_reads)
+        return set_err(STRK_ERR_ARG, "batch: read_begin must run from 0 to n_reads");
+    CU(cudaSetDevice(ctx->device));
+    b->n_reads = n_reads;
+    b->n_loci = n_loci;
+    b->h_read_begin.assign(read_begin, read_begin + n_loci + 1);
+    b->n_general = 0;
+    for (int k = 0; k < STRK_PK_NBIN; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
+    b->max_n1 = b->mb_cols_base = b->mb_m = 0;
+
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+#define UP(buf, dst, src, n) \
+    if (e == cudaSuccess) e = upload(b->buf, &b->dst, src, (size_t)(n), st)
+    UP(arena, d_arena, (const unsigned char *)arena, arena_bytes);
+    UP(seq_off, d_seq_off, (const unsigned long long *)seq_off, n_reads);
+    UP(lens, d_lens, (const int *)lens, 3 * n_reads);
+    UP(est, d_est, (const int *)est_cn, n_reads);
+    UP(read_begin, d_read_begin, (const long long *)read_begin, n_loci + 1);
+    UP(motif_off, d_motif_off, (const unsigned long long *)motif_off, n_loci);
+    UP(motif_len, d_motif_len, (const int *)motif_len, n_loci);
+#undef UP
+    const size_t nr = (size_t)(n_reads ? n_reads : 1);
+    if (e == cudaSuccess) e = b->read_locus.reserve(nr);
+    if (e == cudaSuccess) e = b->order.reserve(nr);
+    if (e == cudaSuccess) e = b->bin.reserve(nr);
+    if (e == cudaSuccess) e = b->out.reserve(nr * 4);
+    if (e == cudaSuccess) e = b->status.reserve((size_t)(n_loci ? n_loci : 1));
+    b->d_read_locus = b->read_locus.p;
+    b->d_order = b->order.p;
+    b->d_out = b->out.p;
+    b->d_status = b->status.p;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "batch upload: %s",
+                       cudaGetErrorString(e));
+    }
+    return batch_plan(ctx, b, arena_bytes);
 }
 
 extern "C" int strk_batch_create(strk_ctx *ctx, strk_batch **out) {
@@ -1009,10 +1028,11 @@ static int dp_tables_to_host(strk_ctx *ctx, bool ref, const std::vector<FamDesc>
     return STRK_OK;
 }
 
-// get_ref_repeat_count (repeats.py:73-192) for a batch of loci.  Phase 1: boundary tables (two sg_qe sweeps
-// per locus, every candidate size of a window at once) + replay of the dual-score search -> l_offset /
-// r_offset.  Phase 2: the final get_repeat_count on the adjusted flanks (score tables + replay).  The
-// replays are look-ups only (replay.cuh) and run on the host here: one per locus, not per read.
+// get_ref_repeat_count (repeats.py:73-192) for a batch of loci, device-resident from upload to results.
+// Phase 1: boundary tables (two sg_qe sweeps per locus, every candidate size of a window at once, general kernel)
+// + the dual-score search replayed one thread per locus -> l_offset / r_offset; loci whose search leaves the
+// window are redone 4x wider.  Phase 2: the final get_repeat_count on the adjusted flanks = the read-path batch
+// machinery (packed kernel, device replay, widening) with one "read" per locus, one run per search-parameter tier.
 extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                                const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
                                const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off,
@@ -1024,133 +1044,183 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
     if (rc) return rc;
     rc = validate_motifs("strk_ref_counts", arena_bytes, motif_off, motif_len, n_loci);
     if (rc) return rc;
+    const int WD_MAX = (STRK_MAX_WINDOW - 1) / 2;
+    std::vector<int> h_wd((size_t)n_loci);
+    int max_wd = 8, max_n1 = 0, mb_cols = 0, mb_m = 0;
     for (int64_t l = 0; l < n_loci; ++l) {
         if (start_count[l] < 0 || start_count[l] > (1 << 22) || rc_params[3 * l] < 0 || rc_params[3 * l + 1] < 0 ||
             rc_params[3 * l + 2] < 0 || rc_params[3 * l + 1] > 1000 || rc_params[3 * l + 2] > 1000)
             return set_err(STRK_ERR_ARG, "strk_ref_counts: bad start count / search parameters for locus %lld", (long long)l);
+        h_wd[(size_t)l] = std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
+        max_wd = std::max(max_wd, h_wd[(size_t)l]);
+        const int n1 = lens[3 * l] + lens[3 * l + 1] + lens[3 * l + 2];
+        max_n1 = std::max(max_n1, n1);
+        if (n1 > 32 * 16) {  // multi-pass reads of the general kernel keep a boundary row per candidate column
+            mb_cols = std::max(mb_cols, std::max(lens[3 * l], lens[3 * l + 2]) + motif_len[l] * start_count[l]);
+            mb_m = std::max(mb_m, motif_len[l]);
+        }
     }
     CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
-    TmpDev tmp;
-    unsigned char *d_arena = nullptr;
-    if (tmp.up(&d_arena, arena, (size_t)arena_bytes) != cudaSuccess) {
+    const size_t n = (size_t)n_loci;
+    const bool timing = getenv("STRK_REF_TIMING") != nullptr;  // coarse phase timers on stderr (tuning only)
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    // ---- device-resident inputs and per-locus state (context-owned, recycled across calls)
+    cudaError_t e = ctx->ref_arena.reserve((size_t)arena_bytes);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = ctx->ref_u64[k].reserve(n);
+    const size_t isz[12] = {3 * n, n, n, 3 * n, n, n, n, n, n, n, n, 4};
+    for (int k = 0; k < 12 && e == cudaSuccess; ++k) e = ctx->ref_i[k].reserve(isz[k]);
+    if (e != cudaSuccess) {
         cudaGetLastError();
-        return set_err(STRK_ERR_NOMEM, "strk_ref_counts: cannot upload the arena");
+        return set_err(STRK_ERR_NOMEM, "strk_ref_counts: %s", cudaGetErrorString(e));
     }
-    std::vector<int> l_off((size_t)n_loci, 0), r_off((size_t)n_loci, 0), n_off_scores((size_t)n_loci, 0);
-    SeenSet seen;
-    const int WD_MAX = (STRK_MAX_WINDOW - 1) / 2;
+    unsigned char *d_arena = ctx->ref_arena.p;
+    unsigned long long *d_seq_off = ctx->ref_u64[0].p, *d_motif_off = ctx->ref_u64[1].p;
+    int *d_lens = ctx->ref_i[0].p, *d_start = ctx->ref_i[1].p, *d_ref_size = ctx->ref_i[2].p, *d_rc = ctx->ref_i[3].p;
+    int *d_motif_len = ctx->ref_i[4].p, *d_wd = ctx->ref_i[5].p, *d_l_off = ctx->ref_i[6].p, *d_r_off = ctx->ref_i[7].p;
+    int *d_n_off = ctx->ref_i[8].p, *d_ids_a = ctx->ref_i[9].p, *d_ids_b = ctx->ref_i[10].p;
+    unsigned int *d_cnt = (unsigned int *)ctx->ref_i[11].p;
+    CU(cudaMemcpyAsync(d_arena, arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_seq_off, seq_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_motif_off, motif_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_lens, lens, 3 * n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_start, start_count, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ref_size, ref_size, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rc, rc_params, 3 * n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_motif_len, motif_len, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_wd, h_wd.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_l_off, 0, n * sizeof(int), st));
+    CU(cudaMemsetAsync(d_r_off, 0, n * sizeof(int), st));
+    CU(cudaMemsetAsync(d_n_off, 0, n * sizeof(int), st));
+    const int T = 128;
 
     // ---- phase 1: boundary extension (skipped with respect_coords, repeats.py:99)
     if (!respect_coords) {
-        std::vector<int64_t> pending((size_t)n_loci);
-        std::vector<int> wd((size_t)n_loci);
-        for (int64_t l = 0; l < n_loci; ++l) {
-            pending[(size_t)l] = l;
-            wd[(size_t)l] = std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
-        }
-        while (!pending.empty()) {
-            std::vector<FamDesc> fams(pending.size());
-            size_t total = 0;
-            for (size_t q = 0; q < pending.size(); ++q) {
-                const int64_t l = pending[q];
-                FamDesc &f = fams[q];
-                f.db_off = seq_off[l];
-                f.motif_off = motif_off[l];
-                f.n_fl = lens[3 * l], f.n_tr = lens[3 * l + 1], f.n_fr = lens[3 * l + 2], f.m = motif_len[l];
-                // size 0 with an empty flank would be an empty candidate; the replay reports it if it gets there
-                const int lo_min = (f.n_fl == 0 || f.n_fr == 0) ? 1 : 0;
-                f.n_lo = std::max(lo_min, start_count[l] - wd[(size_t)l]);
-                f.n_hi = std::max(f.n_lo, start_count[l] + wd[(size_t)l]);
-                f.out_off = total;
-                total += (size_t)(f.n_hi - f.n_lo + 1);
+        long long n_pending = n_loci;
+        const int *d_ids = nullptr;
+        int *d_again = d_ids_a;
+        int cur_wd = max_wd;
+        while (n_pending > 0) {
+            const int stride_w = 2 * cur_wd + 1;
+            if (ctx->fams.reserve((size_t)n_pending) != cudaSuccess ||
+                ctx->table64.reserve((size_t)n_pending * (size_t)stride_w * 2) != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(STRK_ERR_NOMEM, "strk_ref_counts: cannot allocate the boundary tables");
             }
-            std::vector<long long> keys;
-            rc = dp_tables_to_host<long long>(ctx, true, fams, d_arena, total * 2, keys);
+            ref_plan1_kernel<<<(unsigned)((n_pending + T - 1) / T), T, 0, st>>>(d_ids, (int)n_pending, d_seq_off, d_lens,
+                                                                                d_start, d_wd, d_motif_off, d_motif_len,
+                                                                                stride_w, ctx->fams.p);
+            CU(cudaGetLastError());
+            const int b_len = max_n1 + 2;
+            const int rowlen = max_n1 > 32 * 16 ? mb_cols + mb_m * cur_wd + 2 : 2;
+            rc = launch_general(ctx, true, ctx->fams.p, nullptr, n_pending, d_arena, ctx->table64.p, b_len, rowlen, st);
             if (rc) return rc;
-            std::vector<int64_t> again;
-            for (size_t q = 0; q < pending.size(); ++q) {
-                const int64_t l = pending[q];
-                const FamDesc &f = fams[q];
-                RefClimbResult cr = climb_ref(keys.data() + 2 * f.out_off, f.n_lo, f.n_hi, start_count[l], rc_params[3 * l],
-                                              rc_params[3 * l + 1], rc_params[3 * l + 2], f.n_fl, f.n_fr, ref_size[l],
-                                              vcf_anchor_size, seen);
-                if (cr.status == 1) {
-                    if (wd[(size_t)l] >= WD_MAX)
-                        return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld left the widest window", (long long)l);
-                    wd[(size_t)l] = std::min(WD_MAX, wd[(size_t)l] * 4);
-                    again.push_back(l);
-                    ctx->stats[5] += 1;
-                    continue;
-                }
-                if (cr.status == 2)
-                    return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld scored no size (max_iters = %d)",
-                                   (long long)l, rc_params[3 * l]);
-                l_off[(size_t)l] = cr.l_offset;
-                r_off[(size_t)l] = cr.r_offset;
-                n_off_scores[(size_t)l] = cr.n_offset_scores;
+            CU(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned int), st));
+            ref_replay1_kernel<<<(unsigned)((n_pending + T - 1) / T), T, 0, st>>>(
+                d_ids, (int)n_pending, ctx->table64.p, ctx->fams.p, d_start, d_rc, d_ref_size, vcf_anchor_size, WD_MAX, d_wd,
+                d_l_off, d_r_off, d_n_off, d_again, d_cnt);
+            CU(cudaGetLastError());
+            ctx->stats[2] += 2;
+            unsigned int h_cnt[4] = {0, 0, 0, 0};
+            CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (h_cnt[2])
+                return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld left the widest window",
+                               (long long)(0x7fffffffu - h_cnt[2]));
+            if (h_cnt[1]) {
+                const long long l = (long long)(0x7fffffffu - h_cnt[1]);
+                return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld scored no size (max_iters = %d)", l,
+                               rc_params[3 * l]);
             }
-            pending.swap(again);
+            n_pending = h_cnt[0];
+            ctx->stats[5] += (double)n_pending;
+            d_ids = d_again;
+            d_again = d_again == d_ids_a ? d_ids_b : d_ids_a;
+            cur_wd = std::min(WD_MAX, cur_wd * 4);
         }
     }
+    const double t_phase1 = now();
+    std::vector<int> l_off(n), r_off(n), n_off(n);
+    CU(cudaMemcpyAsync(l_off.data(), d_l_off, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(r_off.data(), d_r_off, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(n_off.data(), d_n_off, n * sizeof(int), cudaMemcpyDeviceToHost, st));
 
-    // ---- phase 2: final count on the adjusted flanks (repeats.py:171-188)
-    {
-        std::vector<int64_t> pending((size_t)n_loci);
-        std::vector<int> wd((size_t)n_loci), start2((size_t)n_loci), nfl2((size_t)n_loci), nfr2((size_t)n_loci);
-        for (int64_t l = 0; l < n_loci; ++l) {
-            pending[(size_t)l] = l;
-            wd[(size_t)l] = std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
-            const int mov_l = std::max(0, l_off[(size_t)l]), mov_r = std::max(0, r_off[(size_t)l]);
-            nfl2[(size_t)l] = lens[3 * l] - mov_l;
-            nfr2[(size_t)l] = lens[3 * l + 2] - mov_r;
-            const int m = motif_len[l];
-            // round() of the float quotient: banker's rounding (repeats.py:182)
-            start2[(size_t)l] = (int)nearbyint(((double)start_count[l] * (double)m + (double)(mov_l + mov_r)) / (double)m);
+    // ---- phase 2: final count on the adjusted flanks (repeats.py:171-188), one batch run per parameter tier
+    std::vector<std::vector<int>> tiers;
+    std::vector<int> tier_key;  // 3 ints per tier
+    for (int64_t l = 0; l < n_loci; ++l) {
+        size_t t = 0;
+        for (; t < tiers.size(); ++t)
+            if (tier_key[3 * t] == rc_params[3 * l] && tier_key[3 * t + 1] == rc_params[3 * l + 1] &&
+                tier_key[3 * t + 2] == rc_params[3 * l + 2])
+                break;
+        if (t == tiers.size()) {
+            tiers.emplace_back();
+            tier_key.insert(tier_key.end(), rc_params + 3 * l, rc_params + 3 * l + 3);
         }
-        while (!pending.empty()) {
-            std::vector<FamDesc> fams(pending.size());
-            size_t total = 0;
-            for (size_t q = 0; q < pending.size(); ++q) {
-                const int64_t l = pending[q];
-                FamDesc &f = fams[q];
-                const int n1 = lens[3 * l] + lens[3 * l + 1] + lens[3 * l + 2];
-                f.db_off = seq_off[l];
-                f.motif_off = motif_off[l];
-                f.n_fl = nfl2[(size_t)l], f.n_fr = nfr2[(size_t)l], f.n_tr = n1 - f.n_fl - f.n_fr, f.m = motif_len[l];
-                const int lo_min = (f.n_fl + f.n_fr == 0) ? 1 : 0;
-                f.n_lo = std::max(lo_min, start2[(size_t)l] - wd[(size_t)l]);
-                f.n_hi = std::max(f.n_lo, start2[(size_t)l] + wd[(size_t)l]);
-                f.out_off = total;
-                total += (size_t)(f.n_hi - f.n_lo + 1);
-            }
-            std::vector<int> scores;
-            rc = dp_tables_to_host<int>(ctx, false, fams, d_arena, total, scores);
-            if (rc) return rc;
-            std::vector<int64_t> again;
-            for (size_t q = 0; q < pending.size(); ++q) {
-                const int64_t l = pending[q];
-                const FamDesc &f = fams[q];
-                ClimbResult cr = climb_single(scores.data() + f.out_off, f.n_lo, f.n_hi, start2[(size_t)l], rc_params[3 * l],
-                                              rc_params[3 * l + 1], rc_params[3 * l + 2], ctx->tie_flags, seen);
-                if (cr.status == 1) {
-                    if (wd[(size_t)l] >= WD_MAX)
-                        return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld left the widest window", (long long)l);
-                    wd[(size_t)l] = std::min(WD_MAX, wd[(size_t)l] * 4);
-                    again.push_back(l);
-                    ctx->stats[5] += 1;
-                    continue;
-                }
-                if (cr.status == 2)
-                    return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld scored no size (max_iters = %d)",
-                                   (long long)l, rc_params[3 * l]);
-                int32_t *o = out + 8 * l;
-                o[0] = cr.best_n, o[1] = cr.best_score, o[2] = l_off[(size_t)l], o[3] = r_off[(size_t)l];
-                o[4] = n_off_scores[(size_t)l], o[5] = cr.n_explored, o[6] = f.n_fl, o[7] = f.n_fr;
-            }
-            pending.swap(again);
+        tiers[t].push_back((int)l);
+    }
+    if (!ctx->ref_batch) ctx->ref_batch = new (std::nothrow) strk_batch();
+    if (!ctx->ref_batch) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    strk_batch *b = ctx->ref_batch;
+    std::vector<int> res;
+    for (size_t t = 0; t < tiers.size(); ++t) {
+        const std::vector<int> &ids = tiers[t];
+        const size_t nt = ids.size();
+        e = b->seq_off.reserve(nt);
+        if (e == cudaSuccess) e = b->lens.reserve(3 * nt);
+        if (e == cudaSuccess) e = b->est.reserve(nt);
+        if (e == cudaSuccess) e = b->motif_off.reserve(nt);
+        if (e == cudaSuccess) e = b->motif_len.reserve(nt);
+        if (e == cudaSuccess) e = b->read_begin.reserve(nt + 1);
+        if (e == cudaSuccess) e = b->read_locus.reserve(nt);
+        if (e == cudaSuccess) e = b->order.reserve(nt);
+        if (e == cudaSuccess) e = b->bin.reserve(nt);
+        if (e == cudaSuccess) e = b->out.reserve(nt * 4);
+        if (e == cudaSuccess) e = b->status.reserve(nt);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(STRK_ERR_NOMEM, "strk_ref_counts: %s", cudaGetErrorString(e));
+        }
+        b->n_reads = b->n_loci = (long long)nt;
+        b->d_arena = d_arena;
+        b->d_seq_off = b->seq_off.p, b->d_lens = b->lens.p, b->d_est = b->est.p, b->d_motif_off = b->motif_off.p;
+        b->d_motif_len = b->motif_len.p, b->d_read_begin = b->read_begin.p, b->d_read_locus = b->read_locus.p;
+        b->d_order = b->order.p, b->d_out = b->out.p, b->d_status = b->status.p;
+        b->h_read_begin.resize(nt + 1);
+        for (size_t q = 0; q <= nt; ++q) b->h_read_begin[q] = (long long)q;
+        b->n_general = 0;
+        for (int k = 0; k < STRK_PK_NBIN; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
+        b->max_n1 = b->mb_cols_base = b->mb_m = 0;
+        CU(cudaMemcpyAsync(d_ids_a, ids.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        ref_plan2_kernel<<<(unsigned)((nt + T - 1) / T), T, 0, st>>>(d_ids_a, (int)nt, d_seq_off, d_lens, d_start, d_motif_off,
+                                                                     d_motif_len, d_l_off, d_r_off, b->d_seq_off, b->d_lens,
+                                                                     b->d_est, b->d_motif_off, b->d_motif_len,
+                                                                     b->d_read_begin);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));  // `ids` is read by the copy above
+        rc = batch_plan(ctx, b, arena_bytes);
+        if (rc) return rc;
+        const double widened = ctx->stats[5];
+        rc = strk_batch_run(ctx, b, tier_key[3 * t], tier_key[3 * t + 1], tier_key[3 * t + 2], STRK_KERNEL_AUTO, nullptr);
+        if (rc) return rc;
+        ctx->stats[5] += widened;
+        res.resize(nt * 4);
+        CU(cudaMemcpy(res.data(), b->d_out, nt * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t q = 0; q < nt; ++q) {
+            const int l = ids[q];
+            int32_t *o = out + 8 * (size_t)l;
+            o[0] = res[4 * q], o[1] = res[4 * q + 1], o[2] = l_off[(size_t)l], o[3] = r_off[(size_t)l];
+            o[4] = n_off[(size_t)l], o[5] = res[4 * q + 2];
+            o[6] = lens[3 * l] - std::max(0, l_off[(size_t)l]);
+            o[7] = lens[3 * l + 2] - std::max(0, r_off[(size_t)l]);
         }
     }
+    if (timing)
+        fprintf(stderr, "[strk_ref_counts] %lld loci: upload + phase 1 %.2f ms, phase 2 %.2f ms\n", (long long)n_loci,
+                t_phase1 - t_begin, now() - t_phase1);
     return STRK_OK;
 }
 
