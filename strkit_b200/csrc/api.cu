@@ -95,7 +95,7 @@ struct strk_ctx {
     // reference path (strk_ref_counts): per-locus arrays, pending lists, and the one-read-per-locus batch of phase 2
     DevBuf<unsigned char> ref_arena;
     DevBuf<unsigned long long> ref_u64[2];
-    DevBuf<int> ref_i[12];
+    DevBuf<int> ref_i[13];
     struct strk_batch *ref_batch = nullptr;
     DevBuf<int> al_i[8];             //                 per-read / per-locus integer arrays (recycled across calls)
     DevBuf<double> al_d[3];
@@ -262,7 +262,7 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     ctx->ref_batch = nullptr;
     ctx->ref_arena.release();
     for (int k = 0; k < 2; ++k) ctx->ref_u64[k].release();
-    for (int k = 0; k < 12; ++k) ctx->ref_i[k].release();
+    for (int k = 0; k < 13; ++k) ctx->ref_i[k].release();
     ctx->scratch.release();
     ctx->fams.release();
     ctx->table.release();
@@ -382,7 +382,7 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
 // ------------------------------------------------------------------------------------------------
 template <int R>
 static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
-                           int *table, PackedDims dims, cudaStream_t st) {
+                           int *table, PackedDims dims, cudaStream_t st, int ref_mode) {
     size_t smem = pk_smem_bytes(R, dims);
     if (const char *env = getenv("STRK_PK_EXTRA_SMEM")) smem += (size_t)atoi(env);  // occupancy experiments only
     static size_t configured = 0;
@@ -403,17 +403,18 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
     }
     dp_packed_kernel<R><<<(unsigned)grid, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
                                                                      ctx->pk_scratch.p, ctx->fallback.p,
-                                                                     ctx->d_queue + 2);
+                                                                     ctx->d_queue + 2, ref_mode);
     CU(cudaGetLastError());
     ctx->stats[2] += 1;
     return STRK_OK;
 }
 
+// ref_mode: the families are reference windows and `table` holds the 64-bit boundary keys (score_ref_boundaries)
 static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
-                         int *table, PackedDims dims, cudaStream_t st) {
+                         int *table, PackedDims dims, cudaStream_t st, int ref_mode = 0) {
     switch (R) {
 #define PK_CASE(N) \
-    case N: return launch_packed_r<N>(ctx, fams, list, n, arena, table, dims, st);
+    case N: return launch_packed_r<N>(ctx, fams, list, n, arena, table, dims, st, ref_mode);
         PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8) PK_CASE(9) PK_CASE(10) PK_CASE(11)
         PK_CASE(12) PK_CASE(13) PK_CASE(14) PK_CASE(15) PK_CASE(16)
 #undef PK_CASE
@@ -1070,8 +1071,8 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
     // ---- device-resident inputs and per-locus state (context-owned, recycled across calls)
     cudaError_t e = ctx->ref_arena.reserve((size_t)arena_bytes);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = ctx->ref_u64[k].reserve(n);
-    const size_t isz[12] = {3 * n, n, n, 3 * n, n, n, n, n, n, n, n, 4};
-    for (int k = 0; k < 12 && e == cudaSuccess; ++k) e = ctx->ref_i[k].reserve(isz[k]);
+    const size_t isz[13] = {3 * n, n, n, 3 * n, n, n, n, n, n, n, n, 4, n};
+    for (int k = 0; k < 13 && e == cudaSuccess; ++k) e = ctx->ref_i[k].reserve(isz[k]);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "strk_ref_counts: %s", cudaGetErrorString(e));
@@ -1115,8 +1116,63 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
             CU(cudaGetLastError());
             const int b_len = max_n1 + 2;
             const int rowlen = max_n1 > 32 * 16 ? mb_cols + mb_m * cur_wd + 2 : 2;
-            rc = launch_general(ctx, true, ctx->fams.p, nullptr, n_pending, d_arena, ctx->table64.p, b_len, rowlen, st);
-            if (rc) return rc;
+            if (d_ids == nullptr && ctx->h_consts.packed_ok && 2 * stride_w <= PK_WINDOW_MAX) {
+                // first pass (locus q = q): packed kernel in reference mode per rows-per-lane class, the forward and
+                // the reverse sg_qe alignment of a locus in the two halves of its lane words; the rest -> general
+                std::vector<int> lists[STRK_PK_NBIN];
+                int mmax[STRK_PK_NBIN] = {0}, flank[STRK_PK_NBIN] = {0};
+                for (int64_t l = 0; l < n_loci; ++l) {
+                    const int fl = lens[3 * l], tr = lens[3 * l + 1], fr = lens[3 * l + 2], m = motif_len[l];
+                    int R = strk_pick_rows_packed(fl + tr + fr + 1);
+                    if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128) R = 0;
+                    lists[R].push_back((int)l);
+                    mmax[R] = std::max(mmax[R], m);
+                    flank[R] = std::max(flank[R], std::max(fl, fr));
+                }
+                std::vector<int> flat;
+                size_t at[STRK_PK_NBIN];
+                for (int k = 0; k < STRK_PK_NBIN; ++k) {
+                    at[k] = flat.size();
+                    flat.insert(flat.end(), lists[k].begin(), lists[k].end());
+                }
+                int *d_lists = ctx->ref_i[12].p;
+                if (ctx->fallback.reserve(n) != cudaSuccess) {
+                    cudaGetLastError();
+                    return set_err(STRK_ERR_NOMEM, "strk_ref_counts: cannot allocate the fallback list");
+                }
+                CU(cudaMemcpyAsync(d_lists, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+                CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
+                long long n_packed = 0;
+                for (int k = STRK_PK_RMAX; k >= 1; --k) {
+                    if (lists[k].empty()) continue;
+                    PackedDims dims;
+                    dims.colt_entries = flank[k] + 64;
+                    dims.prof_words = pk_prof_words(k, mmax[k]);
+                    dims.w_max = 2 * stride_w - 1;  // forward + reverse columns of every size of the window
+                    if (pk_smem_bytes(k, dims) > 200 * 1024) {
+                        rc = launch_general(ctx, true, ctx->fams.p, d_lists + at[k], (long long)lists[k].size(), d_arena,
+                                            ctx->table64.p, b_len, rowlen, st);
+                        if (rc) return rc;
+                        continue;
+                    }
+                    rc = launch_packed(ctx, k, ctx->fams.p, d_lists + at[k], (int)lists[k].size(), d_arena,
+                                       (int *)ctx->table64.p, dims, st, 1);
+                    if (rc) return rc;
+                    n_packed += (long long)lists[k].size();
+                }
+                rc = launch_general(ctx, true, ctx->fams.p, d_lists + at[0], (long long)lists[0].size(), d_arena,
+                                    ctx->table64.p, b_len, rowlen, st);
+                if (rc) return rc;
+                if (n_packed) {
+                    rc = launch_general(ctx, true, ctx->fams.p, ctx->fallback.p, n_packed, d_arena, ctx->table64.p, b_len,
+                                        rowlen, st, ctx->d_queue + 2);
+                    if (rc) return rc;
+                }
+                CU(cudaStreamSynchronize(st));  // `flat` is read by the copy above
+            } else {
+                rc = launch_general(ctx, true, ctx->fams.p, nullptr, n_pending, d_arena, ctx->table64.p, b_len, rowlen, st);
+                if (rc) return rc;
+            }
             CU(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned int), st));
             ref_replay1_kernel<<<(unsigned)((n_pending + T - 1) / T), T, 0, st>>>(
                 d_ids, (int)n_pending, ctx->table64.p, ctx->fams.p, d_start, d_rc, d_ref_size, vcf_anchor_size, WD_MAX, d_wd,

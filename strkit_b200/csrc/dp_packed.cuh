@@ -116,6 +116,8 @@ struct PkState {
     int poff;       // word offset of the current profile column (motif phase)
     int cand_step;  // step at which this lane reaches the next forward candidate column
     unsigned foff;  // next forward capture slot: uint4 index into the warp's scratch (lane offset applied)
+    int cand_stepB;  // the same for the backward half (read mode: one column; reference mode: one per size)
+    unsigned boff;
 };
 
 // One column of the wavefront -> scratch: H[0..R) then the prefix-max word, word w of the column at
@@ -165,8 +167,8 @@ template <int R, int CORE, bool FC, bool BC>
 __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, const bool lane0, const int lane,
                                        const unsigned one, const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ ctp,
                                        const unsigned *__restrict__ prof_lane, const int pstride, const int pwrap,
-                                       const int m, const int last_cand_step, const int bstep,
-                                       uint4 *__restrict__ scr, uint4 *__restrict__ dstB) {
+                                       const int m, const int last_cand_step, const int last_cand_stepB,
+                                       uint4 *__restrict__ scr) {
     constexpr int QN = (R + 1 + 3) / 4;
 #pragma unroll 1
     for (; s < s_end; ++s) {
@@ -223,18 +225,6 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
             }
         }
         st.pm = __viaddmax_u16x2(st.pm, ginc, st.H[R - 1]);
-#ifdef PK_BRANCHY_CAPTURE
-        if (FC) {
-            if (s == st.cand_step) {
-                pk_capture<R>(st, scr + st.foff, 1u);
-                st.foff += QN * 32;
-                st.cand_step = st.cand_step + m > last_cand_step ? 0x7fffffff : st.cand_step + m;
-            }
-        }
-        if (BC) {
-            if (s == bstep) pk_capture<R>(st, dstB, 1u);
-        }
-#else
         if (FC) {  // predicated, not branched: some lane captures in almost every step of the candidate region
             const bool hit = s == st.cand_step;
             pk_capture<R>(st, scr + st.foff, hit ? 1u : 0u);
@@ -242,8 +232,13 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
             st.foff += hit ? QN * 32 : 0;
             st.cand_step = hit ? (nxt > last_cand_step ? 0x7fffffff : nxt) : st.cand_step;
         }
-        if (BC) pk_capture<R>(st, dstB, s == bstep ? 1u : 0u);
-#endif
+        if (BC) {
+            const bool hit = s == st.cand_stepB;
+            pk_capture<R>(st, scr + st.boff, hit ? 1u : 0u);
+            const int nxt = st.cand_stepB + m;
+            st.boff += hit ? QN * 32 : 0;
+            st.cand_stepB = hit ? (nxt > last_cand_stepB ? 0x7fffffff : nxt) : st.cand_stepB;
+        }
     }
 }
 
@@ -252,7 +247,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32, PK_MIN_CTAS(R))
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
                  int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
-                 int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count) {
+                 int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count, int ref_mode) {
     static_assert(R >= 2 && R <= STRK_PK_RMAX, "rows per lane out of range");
     constexpr int N = 32 * R;
     constexpr int QN = (R + 1 + 3) / 4;
@@ -275,7 +270,9 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const int warp_global = blockIdx.x * PK_WARPS + warp;
     const int total_warps = gridDim.x * PK_WARPS;
     const int g = consts->gap;
-    const int flags = consts->end_flags;
+    // reference mode (score_ref_boundaries, repeats.py:23-43): the two halves are the two sg_qe alignments of a
+    // locus -- every begin penalised, nothing combined; `table` then holds 64-bit (score, end_query) keys
+    const int flags = ref_mode ? 0 : consts->end_flags;
     const bool one_table_ok = consts->one_table_ok != 0;
 #if PK_ONE_VREG
     const unsigned one = consts->one_v[lane];  // per-lane load: stays in a vector register
@@ -306,19 +303,23 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         const unsigned char *db = arena + f.db_off;
         const unsigned char *motif = arena + f.motif_off;
 
-        // split of the tract: b0 copies go to the backward half
+        // read mode: split of the tract, b0 copies go to the backward half, candidate n = a + b0.
+        // reference mode: both halves sweep the whole prefix chain and are captured at every size of the window.
         int b0 = (m * f.n_hi + f.n_fl - f.n_fr + m) / (2 * m);
         b0 = b0 < 0 ? 0 : (b0 > f.n_lo ? f.n_lo : b0);
+        if (ref_mode) b0 = 0;
         const int a_lo = f.n_lo - b0, a_hi = f.n_hi - b0;
         const int nW = a_hi - a_lo + 1;
+        const int nWB = ref_mode ? nW : 1;  // captured columns of the backward half
+        if (ref_mode) b0 = f.n_hi;          // columns of the backward half: reverse(fr) + reverse(motif) * n_hi
         const int colsF = f.n_fl + m * a_hi, colsB = f.n_fr + m * b0;
         const int ncols = colsF > colsB ? colsF : colsB;
         const int Lmax = f.n_fl > f.n_fr ? f.n_fl : f.n_fr;
 
         // ---- eligibility (warp-uniform): anything odd goes to the general kernel
         bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 64 <= dims.colt_entries &&
-                  pk_prof_words(R, m) <= dims.prof_words && m <= 128 && nW <= dims.w_max &&
-                  (g * (N + ncols + 40) + 2 * N + 1024) < 65535;
+                  pk_prof_words(R, m) <= dims.prof_words && m <= 128 && nW + nWB <= dims.w_max + 1 &&
+                  (g * (N + ncols + 40) + 2 * N + 1024) < (ref_mode ? 32000 : 65535);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) {
             if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
@@ -446,17 +447,19 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
         st.poff = 0;
         st.foff = (unsigned)lane;
-        uint4 *dstB = scr + (size_t)nW * (QN * 32) + lane;
+        st.boff = (unsigned)(nW * (QN * 32) + lane);
 
         // step ranges (warp-uniform).  Lane t is at column c during step c + t - 1.
         const int first_cand = f.n_fl + m * a_lo;
         const int nsteps = ncols + 31;
         const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first motif-phase step
         const int fc_begin = first_cand - 1;                         // forward captures: [fc_begin, nsteps)
-        const int bc_begin = colsB - 1, bc_end = colsB + 31;         // backward capture: [bc_begin, bc_end)
+        const int first_candB = colsB - m * (nWB - 1);
+        const int bc_begin = first_candB - 1, bc_end = colsB + 31;   // backward captures: [bc_begin, bc_end)
         st.cand_step = first_cand + lane - 1;
+        st.cand_stepB = first_candB + lane - 1;
         const int last_cand_step = colsF + lane - 1;
-        const int bstep = colsB + lane - 1;
+        const int last_cand_stepB = colsB + lane - 1;
         const uint4 *ctp = colT + 32 - lane;  // ctp[s] = table of the column this lane computes in step s
         const unsigned *prof_lane = prof + 2 * lane;
         const int pstride = RH * 32, pwrap = m * RH * 32;  // in row pairs (uint2)
@@ -464,7 +467,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 
 #define PK_RUN(CORE, FC, BC, END)                                                                          \
     pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, one, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,        \
-                            last_cand_step, bstep, scr, dstB)
+                            last_cand_step, last_cand_stepB, scr)
 
         int s = 0;
         // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
@@ -539,8 +542,41 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
 #undef PK_RUN
 
-        // ---- combine: score(n) for every candidate of the window
         __syncwarp();
+        if (ref_mode) {
+            // ---- reference mode: per size, the best cell of the captured column and the smallest row attaining it
+            // (parasail end_query), for the forward (low halves, slots 0..nW) and the reverse alignment (high halves,
+            // slots nW..2nW).  Key = (score + 32768) << 16 | (0xffff - row): one REDUX per column and direction.
+            long long *out64 = (long long *)table + 2 * f.out_off;
+            for (int w2 = 0; w2 < 2 * nW; ++w2) {
+                const int dir = w2 >= nW, w = dir ? w2 - nW : w2;
+                const int p = (dir ? f.n_fr : f.n_fl) + m * (f.n_lo + w);
+                unsigned key = 0u;
+#pragma unroll
+                for (int q = 0; q < QN; ++q) {
+                    const uint4 v = scr[(unsigned)((w2 * QN + q) * 32 + lane)];
+                    const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 4 * q + j;
+                        if (r < R) {
+                            const int I = lane * R + r + 1, i = I - off;
+                            const int h = (int)(dir ? wv[j] >> 16 : wv[j] & 0xffffu);
+                            const unsigned k = ((unsigned)(h - g * (I + p) + 32768) << 16) | (unsigned)(0xffff - i);
+                            if (i >= 1) key = max(key, k);
+                        }
+                    }
+                }
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane0) {
+                    const int score = (int)(key >> 16) - 32768, row = 0xffff - (int)(key & 0xffffu);
+                    out64[w2] = ((long long)score << 32) | (long long)(unsigned)(0x7fffffff - row);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---- combine: score(n) for every candidate of the window
         const unsigned *scw = (const unsigned *)scr;
         const unsigned bbase = (unsigned)nW * (QN * 128);  // word offset of the backward slot
         unsigned Bv[R];  // backward value paired with each forward row (low half), 0 for pad rows
