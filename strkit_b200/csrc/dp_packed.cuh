@@ -36,6 +36,11 @@
 //
 // Reads this kernel cannot take (IUPAC codes inside the read, value range beyond u16, empty flank) are
 // appended to a fallback list that the general int32 kernel processes afterwards -- still on the GPU.
+//
+// Reference mode (ref_mode != 0): the same sweeps serve score_ref_boundaries (repeats.py:23-43).  The low halves
+// hold the forward sg_qe alignment of a reference window, the high halves the reverse one, both over the whole
+// prefix chain and both captured at every size of the window; instead of combining the halves, the epilogue
+// reduces each captured column to (best score, smallest row attaining it) = parasail's (score, end_query).
 #pragma once
 #include "dp_general.cuh"
 #include "strk_common.cuh"
