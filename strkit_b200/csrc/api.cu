@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -90,7 +91,6 @@ struct strk_ctx {
     DevBuf<long long> list_c;
     DevBuf<int> fallback;            // reads the packed kernel handed to the general kernel
     DevBuf<uint4> pk_scratch;        // captured DP columns of the packed kernel (per resident warp)
-    size_t pk_smem_configured[STRK_PK_NBIN] = {0};  // dynamic shared memory opted into, per rows-per-lane class
     DevBuf<double> al_rep[3];        // allele calling: replicate means / weights / stdevs of one chunk of loci
     DevBuf<unsigned char> al_peaks;  //                 replicate peak counts
     // reference path (strk_ref_counts): per-locus arrays, pending lists, and the one-read-per-locus batch of phase 2
@@ -386,10 +386,17 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
                            int *table, PackedDims dims, cudaStream_t st, int ref_mode) {
     size_t smem = pk_smem_bytes(R, dims);
     if (const char *env = getenv("STRK_PK_EXTRA_SMEM")) smem += (size_t)atoi(env);  // occupancy experiments only
-    // the opt-in shared-memory size is a per-device function attribute: remembered per context, not per process
-    if (smem > ctx->pk_smem_configured[R]) {
-        CU(cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->pk_smem_configured[R] = smem;
+    // the opt-in shared-memory size is a per-device attribute of the function, shared by every context of the
+    // process on that device (the streamed path keeps two): only ever raised, under a lock
+    {
+        static std::mutex mu;
+        static size_t configured[64] = {0};
+        std::lock_guard<std::mutex> lock(mu);
+        size_t &cur = configured[ctx->device & 63];
+        if (smem > cur) {
+            CU(cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
     }
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_packed_kernel<R>, PK_WARPS * 32, smem));
