@@ -101,6 +101,27 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` summary (profiles/, a separate run under the profiler; None if the file is not there)."""
+    import re
+
+    path = os.path.join(ROOT, "profiles", "r1_full_packed_v7.txt")
+    if not os.path.exists(path):
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, kernel = 0.0, None
+    for line in open(path):
+        if line.startswith("# kernel:"):
+            if kernel is not None:
+                break  # first kernel of the capture only
+            kernel = line.split(":", 1)[1].strip().split("(")[0]
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+(\w+)\s+([0-9.]+)", line)
+        if m and kernel is not None:
+            total += float(m.group(3)) * unit.get(m.group(2), 1.0)
+    return (total or None), f"{kernel}, one launch, profiles/r1_full_packed_v7.txt"
+
+
 def cpu_baseline(batch, n_loci_sample, steps=1):
     """The oracle (port of the reference's CPU algorithm) on the first n_loci_sample loci, all host cores."""
     from tests import oracle_lib
@@ -327,6 +348,7 @@ def main():
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         arena_gbs = (host_batches[0].nbytes() * args.steps) / dp_s / 1e9 if dp_s > 0 else 0.0
+        traffic, traffic_src = ncu_dram_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / max(1, args.steps), "higher_is_better": True,
@@ -341,7 +363,10 @@ def main():
             "gcups_executed": exec_cells / (elapsed_ms * 1e-3) / 1e9,
             "gcups_reference_equivalent": ref_cells / (elapsed_ms * 1e-3) / 1e9,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak["dual_pipe"], "unit": "Tiop/s",
-                         "frac": achieved / peak["dual_pipe"] if peak["dual_pipe"] else None, "traffic": None,
+                         "frac": achieved / peak["dual_pipe"] if peak["dual_pipe"] else None, "traffic": traffic,
+                         "traffic_note": f"DRAM bytes ({traffic_src}): mostly write-back of the capture scratch; the "
+                                         "algorithmic bytes of that launch are ~35 MB of read arena"
+                                         if traffic else None,
                          "kernel": "dp_general_kernel" if agg["reads_packed_kernel"] == 0 else "dp_packed_kernel",
                          "ops_per_cell": 4, "kernel_ms_per_step": agg["dp_ms"] / max(1, args.steps),
                          "kernel_share_of_step": agg["dp_ms"] / elapsed_ms if elapsed_ms else None,
