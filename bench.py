@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-loci", type=int, default=768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = the same number of blocks as --steps")
     return ap.parse_args()
 
 
@@ -291,7 +291,7 @@ def main():
     # ---- e2e: host buffers through the C-ABI call (H2D + kernels + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e2e_steps = args.e2e_steps or min(args.steps, 8)
+        e2e_steps = args.e2e_steps or args.steps
         outs = [np.empty((b.n_reads, 4), dtype=np.int32) for b in host_batches]
         for o in outs:
             strkit_b200._native.check(strkit_b200._native.lib.strk_host_register(o.ctypes.data, o.nbytes))
