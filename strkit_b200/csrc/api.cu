@@ -175,6 +175,11 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     }
     if (device < 0 || device >= n_dev) return set_err(STRK_ERR_ARG, "device %d out of range (%d devices)", device, n_dev);
     CU(cudaSetDevice(device));
+    // STRK_BLOCKING_SYNC=1: host threads sleep in stream synchronisation instead of spinning (for boxes with fewer
+    // host cores than ranks x host threads; the streamed path keeps three host threads per GPU busy otherwise)
+    if (getenv("STRK_BLOCKING_SYNC")) {
+        if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+    }
     strk_ctx *ctx = new (std::nothrow) strk_ctx();
     if (!ctx) return set_err(STRK_ERR_NOMEM, "out of host memory");
     ctx->device = device;
