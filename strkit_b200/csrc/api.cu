@@ -399,10 +399,11 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
 // ------------------------------------------------------------------------------------------------
 // packed DP launch (one template instantiation per R; persistent warps, per-warp L2-resident scratch)
 // ------------------------------------------------------------------------------------------------
-template <int R>
+template <int R, int L>
 static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
                            int *table, PackedDims dims, cudaStream_t st, int ref_mode) {
-    size_t smem = pk_smem_bytes(R, dims);
+    constexpr int HALVES = 32 / L;
+    size_t smem = pk_smem_bytes(R, dims, L);
     if (const char *env = getenv("STRK_PK_EXTRA_SMEM")) smem += (size_t)atoi(env);  // occupancy experiments only
     // the opt-in shared-memory size is a per-device attribute of the function, shared by every context of the
     // process on that device (the streamed path keeps two): only ever raised, under a lock
@@ -412,17 +413,17 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
         std::lock_guard<std::mutex> lock(mu);
         size_t &cur = configured[ctx->device & 63];
         if (smem > cur) {
-            CU(cudaFuncSetAttribute(dp_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(dp_packed_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cur = smem;
         }
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_packed_kernel<R>, PK_WARPS * 32, smem));
-    if (per_sm < 1) return set_err(STRK_ERR_CUDA, "packed kernel R=%d does not fit an SM (%zu B shared)", R, smem);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_packed_kernel<R, L>, PK_WARPS * 32, smem));
+    if (per_sm < 1) return set_err(STRK_ERR_CUDA, "packed kernel R=%d L=%d does not fit an SM (%zu B shared)", R, L, smem);
     long long grid = (long long)per_sm * ctx->n_sm;
-    const long long need = ((long long)n + PK_WARPS - 1) / PK_WARPS;
+    const long long need = ((long long)n + PK_WARPS * HALVES - 1) / (PK_WARPS * HALVES);
     if (grid > need) grid = need;
-    const size_t words = pk_scratch_words_per_warp(R, dims.w_max) * (size_t)grid * PK_WARPS;
+    const size_t words = pk_scratch_words_per_unit(R, dims.w_max, L) * (size_t)grid * PK_WARPS * HALVES;
     if (ctx->pk_scratch.reserve((words + 3) / 4) != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", words * 4);
@@ -452,20 +453,53 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
             ctx->l2_window_stream = st;
         }
     }
-    dp_packed_kernel<R><<<(unsigned)grid, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
-                                                                     ctx->pk_scratch.p, ctx->fallback.p,
-                                                                     ctx->d_queue + 2, ref_mode);
+    dp_packed_kernel<R, L><<<(unsigned)grid, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
+                                                                        ctx->pk_scratch.p, ctx->fallback.p,
+                                                                        ctx->d_queue + 2, ref_mode);
     CU(cudaGetLastError());
     ctx->stats[2] += 1;
     return STRK_OK;
 }
 
+// Lanes per read of a rows-per-lane class: reads of the classes up to PK_PAIR_RMAX (db < 32 * PK_PAIR_RMAX bases) are
+// swept two per warp, 16 lanes x 2R rows each (half the skew, half the per-step overhead per read).
+// STRK_PK_PAIRS=0 switches the pairing off (measurement only).
+#define PK_PAIR_RMAX 8
+static int pk_lanes_for_class(int R) {
+    static const bool off = [] {
+        const char *e = getenv("STRK_PK_PAIRS");
+        return e && atoi(e) == 0;
+    }();
+    return (!off && R <= PK_PAIR_RMAX) ? 16 : 32;
+}
+// sizes of the class' shared-memory tables for the lane count it runs with
+static PackedDims pk_dims_for_class(int R, int max_flank, int max_m, int w_max) {
+    const int L = pk_lanes_for_class(R);
+    PackedDims d;
+    d.colt_entries = max_flank + 64;
+    d.prof_words = L == 16 ? pk_prof_words(2 * R, max_m, 16) : pk_prof_words(R, max_m, 32);
+    d.w_max = w_max;
+    return d;
+}
+static size_t pk_smem_for_class(int R, const PackedDims &d) {
+    return pk_lanes_for_class(R) == 16 ? pk_smem_bytes(2 * R, d, 16) : pk_smem_bytes(R, d, 32);
+}
+
 // ref_mode: the families are reference windows and `table` holds the 64-bit boundary keys (score_ref_boundaries)
 static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
                          int *table, PackedDims dims, cudaStream_t st, int ref_mode = 0) {
+    if (pk_lanes_for_class(R) == 16) {
+        switch (R) {
+#define PK_CASE(N) \
+    case N: return launch_packed_r<2 * N, 16>(ctx, fams, list, n, arena, table, dims, st, ref_mode);
+            PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8)
+#undef PK_CASE
+            default: break;
+        }
+    }
     switch (R) {
 #define PK_CASE(N) \
-    case N: return launch_packed_r<N>(ctx, fams, list, n, arena, table, dims, st, ref_mode);
+    case N: return launch_packed_r<N, 32>(ctx, fams, list, n, arena, table, dims, st, ref_mode);
         PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8) PK_CASE(9) PK_CASE(10) PK_CASE(11)
         PK_CASE(12) PK_CASE(13) PK_CASE(14) PK_CASE(15) PK_CASE(16)
 #undef PK_CASE
@@ -740,11 +774,8 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             for (int k = STRK_PK_RMAX; k >= 1; --k) {
                 if (!seg_cnt[k]) continue;
                 const int R = k;
-                PackedDims dims;
-                dims.colt_entries = b->bin_flank[k] + 64;
-                dims.prof_words = pk_prof_words(R, b->bin_mmax[k]);
-                dims.w_max = (W + 3) / 4 * 4;
-                if (pk_smem_bytes(R, dims) > 200 * 1024) {
+                const PackedDims dims = pk_dims_for_class(R, b->bin_flank[k], b->bin_mmax[k], (W + 3) / 4 * 4);
+                if (pk_smem_for_class(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
                     rc = launch_general(ctx, false, ctx->fams.p, seg_list[k], seg_cnt[k], b->d_arena, ctx->table.p, b_len,
                                         rowlen, st);
@@ -973,11 +1004,8 @@ static int tables_common(strk_ctx *ctx, bool ref, const uint8_t *arena, uint64_t
         long long n_packed = 0;
         for (int k = STRK_PK_RMAX; k >= 1; --k) {
             if (lists[k].empty()) continue;
-            PackedDims dims;
-            dims.colt_entries = flank[k] + 64;
-            dims.prof_words = pk_prof_words(k, mmax[k]);
-            dims.w_max = (wmax[k] + 3) / 4 * 4;
-            if (pk_smem_bytes(k, dims) > 200 * 1024) {
+            const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], (wmax[k] + 3) / 4 * 4);
+            if (pk_smem_for_class(k, dims) > 200 * 1024) {
                 rc = launch_general(ctx, false, d_fams, d_lists + offs[k], (long long)lists[k].size(), d_arena, d_table,
                                     b_len, rowlen, ctx->stream);
                 if (rc) return rc;
@@ -1196,11 +1224,9 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
                 long long n_packed = 0;
                 for (int k = STRK_PK_RMAX; k >= 1; --k) {
                     if (lists[k].empty()) continue;
-                    PackedDims dims;
-                    dims.colt_entries = flank[k] + 64;
-                    dims.prof_words = pk_prof_words(k, mmax[k]);
-                    dims.w_max = 2 * stride_w - 1;  // forward + reverse columns of every size of the window
-                    if (pk_smem_bytes(k, dims) > 200 * 1024) {
+                    // w_max: forward + reverse columns of every size of the window
+                    const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], 2 * stride_w - 1);
+                    if (pk_smem_for_class(k, dims) > 200 * 1024) {
                         rc = launch_general(ctx, true, ctx->fams.p, d_lists + at[k], (long long)lists[k].size(), d_arena,
                                             ctx->table64.p, b_len, rowlen, st);
                         if (rc) return rc;

@@ -66,22 +66,24 @@ struct PackedDims {
     int w_max;         // candidate sizes per read
 };
 
+// A read is swept by a UNIT of L lanes: L = 32 (one read per warp) or L = 16 (two reads per warp, side by side: half
+// the wavefront skew and half the per-step overhead per read, for reads short enough that 16 * R rows hold them).
 __host__ __device__ inline int pk_quads(int R) { return (R + 1 + 3) / 4; }  // H[0..R) + the prefix-max word
-// Packed profile of the motif phase: rows in pairs, prof[((k * RH + r / 2) * 32 + lane) * 2 + (r & 1)], so that a
+// Packed profile of the motif phase: rows in pairs, prof[((k * RH + r / 2) * L + lane) * 2 + (r & 1)], so that a
 // step fetches its R scores with RH = ceil(R / 2) conflict-free LDS.64 instead of R LDS.32.
 __host__ __device__ inline int pk_prof_rows(int R) { return (R + 1) / 2 * 2; }
-__host__ __device__ inline int pk_prof_words(int R, int m) { return m * pk_prof_rows(R) * 32; }
-__host__ __device__ inline size_t pk_scratch_words_per_warp(int R, int w_max) {
-    return (size_t)(w_max + 1) * pk_quads(R) * 32 * 4;
+__host__ __device__ inline int pk_prof_words(int R, int m, int L = 32) { return m * pk_prof_rows(R) * L; }
+__host__ __device__ inline size_t pk_scratch_words_per_unit(int R, int w_max, int L = 32) {
+    return (size_t)(w_max + 1) * pk_quads(R) * L * 4;
 }
-// per-warp shared memory: [colT uint4 x colt_entries][prof u32 x prof_words][encoded db + motif bytes]
+// per-unit shared memory: [colT uint4 x colt_entries][prof u32 x prof_words][row symbols + motif bytes]
 // row symbols per register row, forward and backward (pad code on pad rows), then the motif
-__host__ __device__ inline size_t pk_code_bytes(int R) { return (size_t)(64 * R + 128 + 15) / 16 * 16; }
-__host__ __device__ inline size_t pk_smem16_per_warp(int R, const PackedDims &d) {
-    return (size_t)d.colt_entries + ((size_t)d.prof_words * 4 + 15) / 16 + pk_code_bytes(R) / 16;
+__host__ __device__ inline size_t pk_code_bytes(int R, int L = 32) { return (size_t)(2 * L * R + 128 + 15) / 16 * 16; }
+__host__ __device__ inline size_t pk_smem16_per_unit(int R, const PackedDims &d, int L = 32) {
+    return (size_t)d.colt_entries + ((size_t)d.prof_words * 4 + 15) / 16 + pk_code_bytes(R, L) / 16;
 }
-__host__ __device__ inline size_t pk_smem_bytes(int R, const PackedDims &d) {
-    return pk_smem16_per_warp(R, d) * 16 * PK_WARPS;
+__host__ __device__ inline size_t pk_smem_bytes(int R, const PackedDims &d, int L = 32) {
+    return pk_smem16_per_unit(R, d, L) * 16 * PK_WARPS * (32 / L);
 }
 
 // Raw PRMT (generic mode).  NOT __byte_perm: that intrinsic masks the selector with 0x7777, which costs an
@@ -126,7 +128,7 @@ struct PkState {
 };
 
 // One column of the wavefront -> scratch: H[0..R) then the prefix-max word, word w of the column at
-// dst[(w / 4) * 32].{x,y,z,w}.  Full quads go out as predicated 128-bit stores; the tail (R % 4 cells and the
+// dst[(w / 4) * L].{x,y,z,w}.  Full quads go out as predicated 128-bit stores; the tail (R % 4 cells and the
 // prefix maximum) as 64- / 32-bit pieces, so that no register has to be copied into an aligned quad first.
 __device__ __forceinline__ void pk_st4(unsigned *p, unsigned a, unsigned b, unsigned c, unsigned d, unsigned on) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"l"(p), "r"(a),
@@ -141,13 +143,13 @@ __device__ __forceinline__ void pk_st1(unsigned *p, unsigned a, unsigned on) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.global.u32 [%0], %1; }" ::"l"(p), "r"(a), "r"(on) : "memory");
 }
 
-template <int R>
+template <int R, int L>
 __device__ __forceinline__ void pk_capture(const PkState<R> &st, uint4 *__restrict__ dst, const unsigned on) {
     constexpr int QF = R / 4, REM = R % 4;  // full quads, cells in the partial one
 #pragma unroll
     for (int q = 0; q < QF; ++q)
-        pk_st4((unsigned *)(dst + q * 32), st.H[4 * q], st.H[4 * q + 1], st.H[4 * q + 2], st.H[4 * q + 3], on);
-    unsigned *tail = (unsigned *)(dst + QF * 32);
+        pk_st4((unsigned *)(dst + q * L), st.H[4 * q], st.H[4 * q + 1], st.H[4 * q + 2], st.H[4 * q + 3], on);
+    unsigned *tail = (unsigned *)(dst + QF * L);
     if (REM == 1) {
         pk_st2(tail, st.H[R - 1], st.pm, on);
     } else if (REM == 2) {
@@ -166,9 +168,10 @@ __device__ __forceinline__ void pk_capture(const PkState<R> &st, uint4 *__restri
 // FLANK0 = one-table path of a read whose rows are all A/C/G/T (or pad): no addend at all, PRMT + IMAD + VIMNMX3
 enum { PK_CORE_FLANK2 = 0, PK_CORE_FLANK1 = 1, PK_CORE_PROF = 2, PK_CORE_FLANK1R = 3, PK_CORE_FLANK0 = 4 };
 
-// Steps [s, s_end) of the wavefront; lane t computes column s - t + 1 in step s.  CORE selects the score
+// Steps [s, s_end) of the wavefront; lane t of a unit (`lane` here is the lane WITHIN the unit) computes column
+// s - t + 1 in step s.  CORE selects the score
 // source, FC / BC switch the predicated captures of forward candidate columns / the final backward column on.
-template <int R, int CORE, bool FC, bool BC>
+template <int R, int L, int CORE, bool FC, bool BC>
 __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, const bool lane0, const int lane,
                                        const unsigned one, const unsigned tinc, const unsigned ginc, const uint4 *__restrict__ ctp,
                                        const unsigned *__restrict__ prof_lane, const int pstride, const int pwrap,
@@ -177,7 +180,7 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
     constexpr int QN = (R + 1 + 3) / 4;
 #pragma unroll 1
     for (; s < s_end; ++s) {
-        unsigned up_in = __shfl_up_sync(0xffffffffu, st.H[R - 1], 1);
+        unsigned up_in = __shfl_up_sync(0xffffffffu, st.H[R - 1], 1, L);
         st.topv += tinc;
         up_in = lane0 ? st.topv : up_in;
         unsigned d = st.prev_up, u = up_in;
@@ -187,7 +190,7 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
             unsigned sc[(R + 1) / 2 * 2];
 #pragma unroll
             for (int q = 0; q < (R + 1) / 2; ++q) {
-                const uint2 v = pp[q * 32];
+                const uint2 v = pp[q * L];
                 sc[2 * q] = v.x;
                 sc[2 * q + 1] = v.y;
             }
@@ -232,29 +235,31 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
         st.pm = __viaddmax_u16x2(st.pm, ginc, st.H[R - 1]);
         if (FC) {  // predicated, not branched: some lane captures in almost every step of the candidate region
             const bool hit = s == st.cand_step;
-            pk_capture<R>(st, scr + st.foff, hit ? 1u : 0u);
+            pk_capture<R, L>(st, scr + st.foff, hit ? 1u : 0u);
             const int nxt = st.cand_step + m;
-            st.foff += hit ? QN * 32 : 0;
+            st.foff += hit ? QN * L : 0;
             st.cand_step = hit ? (nxt > last_cand_step ? 0x7fffffff : nxt) : st.cand_step;
         }
         if (BC) {
             const bool hit = s == st.cand_stepB;
-            pk_capture<R>(st, scr + st.boff, hit ? 1u : 0u);
+            pk_capture<R, L>(st, scr + st.boff, hit ? 1u : 0u);
             const int nxt = st.cand_stepB + m;
-            st.boff += hit ? QN * 32 : 0;
+            st.boff += hit ? QN * L : 0;
             st.cand_stepB = hit ? (nxt > last_cand_stepB ? 0x7fffffff : nxt) : st.cand_stepB;
         }
     }
 }
 
-template <int R>
+template <int R, int L>
 __global__ void __launch_bounds__(PK_WARPS * 32, PK_MIN_CTAS(R))
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
                  int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
                  int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count, int ref_mode) {
-    static_assert(R >= 2 && R <= STRK_PK_RMAX, "rows per lane out of range");
-    constexpr int N = 32 * R;
+    static_assert(R >= 2 && (L == 32 || L == 16), "rows per lane / lanes per read out of range");
+    constexpr int HALVES = 32 / L;  // reads side by side in one warp
+    constexpr int SK = L - 1;       // wavefront skew: lane t of a unit is t columns behind lane 0
+    constexpr int N = L * R;
     constexpr int QN = (R + 1 + 3) / 4;
     constexpr int RH = (R + 1) / 2;  // row pairs of the packed profile
     extern __shared__ uint4 smem_raw[];
@@ -270,37 +275,48 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     for (int k = threadIdx.x; k <= STRK_SMAT_ROWS; k += blockDim.x) rowinfo[k] = consts->rowinfo[k];
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int wlane = threadIdx.x & 31;
+    const int lane = wlane & (L - 1);  // lane within the unit: everything below is written per unit
+    const int half = wlane / L;
+    const unsigned hmask = L == 32 ? 0xffffffffu : (0xffffu << (16 * half));  // the lanes of my unit
     const int warp = threadIdx.x >> 5;
-    const int warp_global = blockIdx.x * PK_WARPS + warp;
-    const int total_warps = gridDim.x * PK_WARPS;
+    const int unit = warp * HALVES + half;
+    const int unit_global = (blockIdx.x * PK_WARPS + warp) * HALVES + half;
+    const int total_units = gridDim.x * PK_WARPS * HALVES;
     const int g = consts->gap;
-    // reference mode (score_ref_boundaries, repeats.py:23-43): the two halves are the two sg_qe alignments of a
-    // locus -- every begin penalised, nothing combined; `table` then holds 64-bit (score, end_query) keys
+    // reference mode (score_ref_boundaries, repeats.py:23-43): the two halves of a lane word are the two sg_qe
+    // alignments of a locus -- every begin penalised, nothing combined; `table` then holds 64-bit (score, end_query) keys
     const int flags = ref_mode ? 0 : consts->end_flags;
     const bool one_table_ok = consts->one_table_ok != 0;
 #if PK_ONE_VREG
-    const unsigned one = consts->one_v[lane];  // per-lane load: stays in a vector register
+    const unsigned one = consts->one_v[wlane];  // per-lane load: stays in a vector register
 #else
     const unsigned one = consts->one_v[0];  // uniform load
 #endif
     const bool s1_beg = flags & 1, s1_end = flags & 2, s2_beg = flags & 4, s2_end = flags & 8;
     const bool lane0 = lane == 0;
+    // predicate true on every lane of MY unit (the two units of a warp hold different reads)
+    auto all_unit = [&](bool pred) -> bool { return (__ballot_sync(0xffffffffu, pred) & hmask) == hmask; };
 
-    uint4 *colT = smem_raw + (size_t)warp * pk_smem16_per_warp(R, dims);  // entry [j + 31], columns -31 .. Lmax + 31
+    uint4 *colT = smem_raw + (size_t)unit * pk_smem16_per_unit(R, dims, L);  // entry [j + SK], columns -SK .. Lmax + SK
     unsigned *prof = (unsigned *)(colT + dims.colt_entries);
     // symbol codes by REGISTER row (row I of the padded strip, 0-based): rowF[I] = db[I - off], rowB[I] = db[N - 1 - I]
     // (the backward sweep's row), pad code on the pad rows; each lane reads its R consecutive bytes of both
     unsigned char *rowF = (unsigned char *)(prof + (dims.prof_words + 3) / 4 * 4);
     unsigned char *rowB = rowF + N;
     unsigned char *mcodes = rowB + N;
-    uint4 *scr = scratch + (size_t)warp_global * (size_t)(dims.w_max + 1) * QN * 32;
+    uint4 *scr = scratch + (size_t)unit_global * (size_t)(dims.w_max + 1) * QN * L;
     const unsigned tinc = (s2_beg ? (unsigned)g : 0u) | ((s2_end ? (unsigned)g : 0u) << 16);
     const unsigned ginc = (unsigned)g | ((unsigned)g << 16);
     const int g2 = 2 * g;
 
-    for (int fam_idx = warp_global; fam_idx < n_list; fam_idx += total_warps) {
-        const int fam_id = list[fam_idx];
+    const int n_iter = (n_list + total_units - 1) / total_units;  // the same trip count on both units of a warp
+    for (int it = 0; it < n_iter; ++it) {
+        // a unit without a read of its own in the last round re-runs the last read of the list and stores nothing
+        const int fam_idx_raw = unit_global + it * total_units;
+        const bool have = fam_idx_raw < n_list;
+        if (!__any_sync(0xffffffffu, have)) break;
+        const int fam_id = list[have ? fam_idx_raw : n_list - 1];
         const FamDesc f = fams[fam_id];
         const int n1 = f.n_fl + f.n_tr + f.n_fr;
         const int off = N - n1;
@@ -319,45 +335,46 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         if (ref_mode) b0 = f.n_hi;          // columns of the backward half: reverse(fr) + reverse(motif) * n_hi
         const int colsF = f.n_fl + m * a_hi, colsB = f.n_fr + m * b0;
         const int ncols = colsF > colsB ? colsF : colsB;
-        const int Lmax = f.n_fl > f.n_fr ? f.n_fl : f.n_fr;
+        // the flank phase ends for both units of the warp together: the longer flank of the two reads counts
+        const int Lmax = __reduce_max_sync(0xffffffffu, f.n_fl > f.n_fr ? f.n_fl : f.n_fr);
 
-        // ---- eligibility (warp-uniform): anything odd goes to the general kernel
-        bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 64 <= dims.colt_entries &&
-                  pk_prof_words(R, m) <= dims.prof_words && m <= 128 && nW + nWB <= dims.w_max + 1 &&
+        // ---- eligibility (per warp: with two units, both reads go to the general kernel if either is odd)
+        bool ok = off >= 1 && f.n_fl >= 1 && f.n_fr >= 1 && Lmax <= PK_FLANK_MAX && Lmax + 2 * SK + 2 <= dims.colt_entries &&
+                  pk_prof_words(R, m, L) <= dims.prof_words && m <= 128 && nW + nWB <= dims.w_max + 1 &&
                   (g * (N + ncols + 40) + 2 * N + 1024) < (ref_mode ? 32000 : 65535);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) {
-            if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
+            if (lane0 && have) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
             continue;
         }
         __syncwarp();  // the previous read's shared-memory readers are done
 
         // ---- stage the encoded read and motif in shared memory (one coalesced pass over the arena bytes)
         bool motif_acgt = true;
-        for (int d = lane; d < n1; d += 32) {
+        for (int d = lane; d < n1; d += L) {
             const unsigned char c = sc.lut[db[d]];
             rowF[d + off] = c;
             rowB[N - 1 - d] = c;
         }
-        for (int I = lane; I < off; I += 32) rowF[I] = rowB[I] = (unsigned char)STRK_PAD_PEN;
-        for (int k = lane; k < m; k += 32) {
+        for (int I = lane; I < off; I += L) rowF[I] = rowB[I] = (unsigned char)STRK_PAD_PEN;
+        for (int k = lane; k < m; k += L) {
             const unsigned char c = sc.lut[motif[k]];
             mcodes[k] = c;
             motif_acgt = motif_acgt && c < 4;
         }
-        motif_acgt = __all_sync(0xffffffffu, motif_acgt);
+        motif_acgt = all_unit(motif_acgt);
         __syncwarp();
 
         // x % m for 0 <= x < 4096 without a division: x - m * ((x * inv) >> 20), inv = ceil(2^20 / m)
         const unsigned inv_m = (1048576u + (unsigned)m - 1u) / (unsigned)m;
         auto mod_m = [&](int x) -> int { return x - (int)(((unsigned)x * inv_m) >> 20) * m; };
 
-        // ---- per-column PRMT tables for the flank phase: columns -31 .. Lmax + 31 (zero tables for j <= 0).
+        // ---- per-column PRMT tables for the flank phase: columns -SK .. Lmax + SK (zero tables for j <= 0).
         // One-table path: possible when every column symbol of the phase is A/C/G/T (then the score of a
         // non-ACGT row symbol does not depend on the column and rides along as an addend).
         bool acgt = true;
-        for (int e = lane; e <= Lmax + 62; e += 32) {
-            const int j = e - 31;
+        for (int e = lane; e <= Lmax + 2 * SK; e += L) {
+            const int j = e - SK;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (j >= 1) {
                 const int sf = j <= f.n_fl ? rowF[off + j - 1] : mcodes[mod_m(j - f.n_fl - 1)];
@@ -368,7 +385,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             }
             colT[e] = v;
         }
-        const bool cols_acgt = __all_sync(0xffffffffu, acgt);
+        const bool cols_acgt = all_unit(acgt);
 
         // ---- row symbols -> PRMT selectors (one-table format first: the profile build uses it too).  One look-up
         // per row and direction: rowinfo[code] holds the selector nibbles, the class, the addend and the flags.
@@ -386,15 +403,17 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         const bool rows_ok = !(flags_or & 0x800u);
         const bool rows_plain = !(flags_or & 0x1000u);  // A/C/G/T or pad only: no row carries an addend
-        if (!__all_sync(0xffffffffu, rows_ok)) {  // IUPAC code inside the read
-            if (lane0) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
+        if (!__all_sync(0xffffffffu, rows_ok)) {  // IUPAC code inside a read of this warp
+            if (lane0 && have) fallback_list[atomicAdd(fallback_count, 1u)] = fam_id;
             continue;
         }
         // one table per step is enough when the column-independent addend is exact: either every flank-phase
         // column is A/C/G/T (a non-ACGT row then scores the same in every column), or no row carries an addend
-        // (rows all A/C/G/T or pad) -- in which case the step is PRMT + IMAD + VIMNMX3 per cell pair (FLANK0)
+        // (rows all A/C/G/T or pad) -- in which case the step is PRMT + IMAD + VIMNMX3 per cell pair (FLANK0).
+        // The step loops are shared by the units of a warp, so the weaker of their cores is taken.
         const bool no_addend = __all_sync(0xffffffffu, rows_plain);
-        const bool one_table = (one_table_ok && cols_acgt) || no_addend;
+        const bool plain_unit = all_unit(rows_plain);  // evaluated by every lane (it votes across the warp)
+        const bool one_table = __all_sync(0xffffffffu, (one_table_ok && cols_acgt) || plain_unit);
         // ---- packed profile for the motif phase (row pairs, see pk_prof_rows), column j = Lmax + 1 + k (mod m)
         if (one_table_ok && motif_acgt) {
             for (int k = 0; k < m; ++k) {
@@ -402,7 +421,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 const unsigned tb = (unsigned)t8b[mcodes[m - 1 - mod_m(k + Lmax - f.n_fr)]];
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    prof[((k * RH + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = pk_prmt(tf, tb, st.selA[r]) + st.selB[r];
+                    prof[((k * RH + (r >> 1)) * L + lane) * 2 + (r & 1)] = pk_prmt(tf, tb, st.selA[r]) + st.selB[r];
             }
         } else {
             for (int k = 0; k < m; ++k) {
@@ -412,7 +431,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 for (int r = 0; r < R; ++r) {
                     const int vf = sc.smat[myF[r] * STRK_NSYM_ + sf] + g2;
                     const int vb = sc.smat[myB[r] * STRK_NSYM_ + sb] + g2;
-                    prof[((k * RH + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = (unsigned)vf | ((unsigned)vb << 16);
+                    prof[((k * RH + (r >> 1)) * L + lane) * 2 + (r & 1)] = (unsigned)vf | ((unsigned)vb << 16);
                 }
             }
         }
@@ -449,37 +468,38 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
             st.prev_up = (unsigned)vf | ((unsigned)vb << 16);
         }
         st.topv = (unsigned)(g * off) | ((unsigned)(g * off) << 16);  // DP row 0 at column 0 (then + tinc per column)
-        st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on lane 31)
+        st.pm = 0u;    // biased prefix maxima of the last row, both halves (meaningful on the last lane of the unit)
         st.poff = 0;
         st.foff = (unsigned)lane;
-        st.boff = (unsigned)(nW * (QN * 32) + lane);
+        st.boff = (unsigned)(nW * (QN * L) + lane);
 
-        // step ranges (warp-uniform).  Lane t is at column c during step c + t - 1.
+        // step ranges, common to the units of the warp (their union).  Lane t is at column c during step c + t - 1.
         const int first_cand = f.n_fl + m * a_lo;
-        const int nsteps = ncols + 31;
-        const int s_star = Lmax + 31 < nsteps ? Lmax + 31 : nsteps;  // first motif-phase step
-        const int fc_begin = first_cand - 1;                         // forward captures: [fc_begin, nsteps)
         const int first_candB = colsB - m * (nWB - 1);
-        const int bc_begin = first_candB - 1, bc_end = colsB + 31;   // backward captures: [bc_begin, bc_end)
+        const int nsteps = __reduce_max_sync(0xffffffffu, ncols + SK);
+        const int s_star = Lmax + SK < nsteps ? Lmax + SK : nsteps;              // first motif-phase step
+        const int fc_begin = __reduce_min_sync(0xffffffffu, first_cand - 1);    // forward captures: [fc_begin, nsteps)
+        const int bc_begin = __reduce_min_sync(0xffffffffu, first_candB - 1);   // backward captures: [bc_begin, bc_end)
+        const int bc_end = __reduce_max_sync(0xffffffffu, colsB + SK);
         st.cand_step = first_cand + lane - 1;
         st.cand_stepB = first_candB + lane - 1;
         const int last_cand_step = colsF + lane - 1;
         const int last_cand_stepB = colsB + lane - 1;
-        const uint4 *ctp = colT + 32 - lane;  // ctp[s] = table of the column this lane computes in step s
+        const uint4 *ctp = colT + (SK + 1) - lane;  // ctp[s] = table of the column this lane computes in step s
         const unsigned *prof_lane = prof + 2 * lane;
-        const int pstride = RH * 32, pwrap = m * RH * 32;  // in row pairs (uint2)
+        const int pstride = RH * L, pwrap = m * RH * L;  // in row pairs (uint2)
         __syncwarp();
 
 #define PK_RUN(CORE, FC, BC, END)                                                                          \
-    pk_run<R, CORE, FC, BC>(st, s, END, lane0, lane, one, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,        \
-                            last_cand_step, last_cand_stepB, scr)
+    pk_run<R, L, CORE, FC, BC>(st, s, END, lane0, lane, one, tinc, ginc, ctp, prof_lane, pstride, pwrap, m,     \
+                               last_cand_step, last_cand_stepB, scr)
 
         int s = 0;
-        // ---- flank phase (PRMT look-ups).  Steps 0..30 are the ramp-up of lane 31, after which the prefix
-        // maximum of the last row starts from scratch.
+        // ---- flank phase (PRMT look-ups).  Steps 0..SK-1 are the ramp-up of the unit's last lane, after which
+        // the prefix maximum of the last row starts from scratch.
         {
-            // part 0: ramp-up steps 0..30 (captures compiled in; they are rare this early)
-            const int e0 = s_star < 31 ? s_star : 31;
+            // part 0: ramp-up steps (captures compiled in only if one can fire this early)
+            const int e0 = s_star < SK ? s_star : SK;
             const bool ramp_caps = fc_begin < e0 || bc_begin < e0;
             if (no_addend) {
                 if (ramp_caps)
@@ -548,6 +568,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 #undef PK_RUN
 
         __syncwarp();
+        // From here on the two units of a warp may run different trip counts (window sizes): every warp-level
+        // primitive below names only the lanes of the unit (hmask).
         if (ref_mode) {
             // ---- reference mode: per size, the best cell of the captured column and the smallest row attaining it
             // (parasail end_query), for the forward (low halves, slots 0..nW) and the reverse alignment (high halves,
@@ -559,7 +581,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 unsigned key = 0u;
 #pragma unroll
                 for (int q = 0; q < QN; ++q) {
-                    const uint4 v = scr[(unsigned)((w2 * QN + q) * 32 + lane)];
+                    const uint4 v = scr[(unsigned)((w2 * QN + q) * L + lane)];
                     const unsigned wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -572,8 +594,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                         }
                     }
                 }
-                key = __reduce_max_sync(0xffffffffu, key);
-                if (lane0) {
+                key = __reduce_max_sync(hmask, key);
+                if (lane0 && have) {
                     const int score = (int)(key >> 16) - 32768, row = 0xffff - (int)(key & 0xffffu);
                     out64[w2] = ((long long)score << 32) | (long long)(unsigned)(0x7fffffff - row);
                 }
@@ -583,7 +605,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         }
         // ---- combine: score(n) for every candidate of the window
         const unsigned *scw = (const unsigned *)scr;
-        const unsigned bbase = (unsigned)nW * (QN * 128);  // word offset of the backward slot
+        const unsigned bbase = (unsigned)nW * (QN * L * 4);  // word offset of the backward slot
         unsigned Bv[R];  // backward value paired with each forward row (low half), 0 for pad rows
         {
             // forward row If = lane * R + r + 1 pairs with backward row Ib = N + off - If: consecutive, descending,
@@ -593,15 +615,15 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 unsigned v = 0u;
-                if (lane * R + r + 1 >= off) v = scw[bbase + (unsigned)(((rb >> 2) * 32 + lb) * 4 + (rb & 3))] >> 16;
+                if (lane * R + r + 1 >= off) v = scw[bbase + (unsigned)(((rb >> 2) * L + lb) * 4 + (rb & 3))] >> 16;
                 Bv[r] = v;
                 if (--rb < 0) rb = R - 1, --lb;
             }
         }
-        const int bextra = (int)(scw[bbase + (unsigned)(((R >> 2) * 32 + 31) * 4 + (R & 3))] >> 16);
+        const int bextra = (int)(scw[bbase + (unsigned)(((R >> 2) * L + (L - 1)) * 4 + (R & 3))] >> 16);
         constexpr int WB = 4;  // candidates per batch of loads (hides the L2 round trip)
-        for (int g0 = 0; g0 < nW; g0 += 32) {  // 32 candidates at a time: lane w keeps the reduced values of g0 + w
-            const int gend = g0 + 32 < nW ? g0 + 32 : nW;
+        for (int g0 = 0; g0 < nW; g0 += L) {  // L candidates at a time: lane w keeps the reduced values of g0 + w
+            const int gend = g0 + L < nW ? g0 + L : nW;
             unsigned my_v = 0u, my_flast = 0u;
             for (int w0 = g0; w0 < gend; w0 += WB) {
                 uint4 q4[WB][QN];
@@ -609,12 +631,12 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 for (int b = 0; b < WB; ++b) {
                     const int ww = w0 + b < gend ? w0 + b : gend - 1;
 #pragma unroll
-                    for (int q = 0; q < QN; ++q) q4[b][q] = scr[(unsigned)((ww * QN + q) * 32 + lane)];
+                    for (int q = 0; q < QN; ++q) q4[b][q] = scr[(unsigned)((ww * QN + q) * L + lane)];
                 }
 #pragma unroll
                 for (int b = 0; b < WB; ++b) {
                     const int ww = w0 + b;
-                    if (ww >= gend) break;  // warp-uniform
+                    if (ww >= gend) break;  // uniform within the unit
                     unsigned acc = 0u;
 #pragma unroll
                     for (int q = 0; q < QN; ++q) {
@@ -624,14 +646,14 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                         if (4 * q + 2 < R) acc = __viaddmax_u16x2(v.z, Bv[(4 * q + 2) % R], acc);
                         if (4 * q + 3 < R) acc = __viaddmax_u16x2(v.w, Bv[(4 * q + 3) % R], acc);
                     }
-                    const unsigned v = __reduce_max_sync(0xffffffffu, acc & 0xffffu);
-                    // lane 31's prefix-max word of this candidate column (forward half)
+                    const unsigned v = __reduce_max_sync(hmask, acc & 0xffffu);
+                    // the unit's last lane holds the prefix-max word of this candidate column (forward half)
                     const unsigned pmw = (&q4[b][R >> 2].x)[R & 3];
-                    const unsigned flast = __shfl_sync(0xffffffffu, pmw, 31) & 0xffffu;
+                    const unsigned flast = __shfl_sync(hmask, pmw, L - 1, L) & 0xffffu;
                     if (lane == ww - g0) my_v = v, my_flast = flast;
                 }
             }
-            if (g0 + lane < gend) {  // un-bias and close the free-end cases: one candidate per lane, coalesced store
+            if (g0 + lane < gend && have) {  // un-bias and close the free-end cases: one candidate per lane
                 const int p = f.n_fl + m * (a_lo + g0 + lane);
                 int best = (int)my_v - g * (N + off + p + colsB);
                 if (s2_end) best = max(best, (int)my_flast - g * (N + p));
