@@ -418,12 +418,12 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
         }
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_packed_kernel<R, L>, PK_WARPS * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_packed_kernel<R, L>, pk_warps(L) * 32, smem));
     if (per_sm < 1) return set_err(STRK_ERR_CUDA, "packed kernel R=%d L=%d does not fit an SM (%zu B shared)", R, L, smem);
     long long grid = (long long)per_sm * ctx->n_sm;
-    const long long need = ((long long)n + PK_WARPS * HALVES - 1) / (PK_WARPS * HALVES);
+    const long long need = ((long long)n + pk_warps(L) * HALVES - 1) / (pk_warps(L) * HALVES);
     if (grid > need) grid = need;
-    const size_t words = pk_scratch_words_per_unit(R, dims.w_max, L) * (size_t)grid * PK_WARPS * HALVES;
+    const size_t words = pk_scratch_words_per_unit(R, dims.w_max, L) * (size_t)grid * pk_warps(L) * HALVES;
     if (ctx->pk_scratch.reserve((words + 3) / 4) != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", words * 4);
@@ -453,7 +453,7 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
             ctx->l2_window_stream = st;
         }
     }
-    dp_packed_kernel<R, L><<<(unsigned)grid, PK_WARPS * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
+    dp_packed_kernel<R, L><<<(unsigned)grid, pk_warps(L) * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
                                                                         ctx->pk_scratch.p, ctx->fallback.p,
                                                                         ctx->d_queue + 2, ref_mode);
     CU(cudaGetLastError());
@@ -463,14 +463,16 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
 
 // Lanes per read of a rows-per-lane class: reads of the classes up to PK_PAIR_RMAX (db < 32 * PK_PAIR_RMAX bases) are
 // swept two per warp, 16 lanes x 2R rows each (half the skew, half the per-step overhead per read).
-// STRK_PK_PAIRS=0 switches the pairing off (measurement only).
+// Larger classes were measured slower paired (R = 9: -1.2 %, 10: -1.8 %, 12: -3.2 %: 2R rows per lane need 127+
+// registers).  STRK_PK_PAIRS=<largest paired class, 0 = none, at most 8> overrides the default (measurement only).
 #define PK_PAIR_RMAX 8
 static int pk_lanes_for_class(int R) {
-    static const bool off = [] {
+    static const int rmax = [] {
         const char *e = getenv("STRK_PK_PAIRS");
-        return e && atoi(e) == 0;
+        const int v = e ? atoi(e) : PK_PAIR_RMAX;
+        return v < 0 ? 0 : (v > PK_PAIR_RMAX ? PK_PAIR_RMAX : v);
     }();
-    return (!off && R <= PK_PAIR_RMAX) ? 16 : 32;
+    return R <= rmax ? 16 : 32;
 }
 // sizes of the class' shared-memory tables for the lane count it runs with
 static PackedDims pk_dims_for_class(int R, int max_flank, int max_m, int w_max) {

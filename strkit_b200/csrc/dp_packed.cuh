@@ -48,8 +48,12 @@
 #define PK_FLANK_MAX 160  // longest flank the packed kernel stages (reference default flank_size = 70)
 #define PK_WINDOW_MAX 128  // widest window (candidate sizes per read) a batch pass gives to the packed kernel
 #ifndef PK_WARPS
-#define PK_WARPS 4  // warps (= reads in flight) per CTA
+#define PK_WARPS 4  // warps per CTA, one read per warp
 #endif
+#ifndef PK_WARPS_PAIRED
+#define PK_WARPS_PAIRED 4  // warps per CTA when a warp holds two reads (2-warp CTAs were measured no faster)
+#endif
+__host__ __device__ constexpr int pk_warps(int L) { return L == 16 ? PK_WARPS_PAIRED : PK_WARPS; }
 #ifndef PK_PROF_IMAD
 #define PK_PROF_IMAD 0
 #endif
@@ -57,7 +61,7 @@
 #define PK_ONE_VREG 0
 #endif
 #ifndef PK_MIN_CTAS  // occupancy the register allocation is held to (shared memory allows about as many)
-#define PK_MIN_CTAS(R) ((R) <= 10 ? 5 : 4)
+#define PK_MIN_CTAS(R) ((R) <= 10 ? 5 : ((R) <= 18 ? 4 : 3))
 #endif
 
 struct PackedDims {
@@ -83,7 +87,7 @@ __host__ __device__ inline size_t pk_smem16_per_unit(int R, const PackedDims &d,
     return (size_t)d.colt_entries + ((size_t)d.prof_words * 4 + 15) / 16 + pk_code_bytes(R, L) / 16;
 }
 __host__ __device__ inline size_t pk_smem_bytes(int R, const PackedDims &d, int L = 32) {
-    return pk_smem16_per_unit(R, d, L) * 16 * PK_WARPS * (32 / L);
+    return pk_smem16_per_unit(R, d, L) * 16 * pk_warps(L) * (32 / L);
 }
 
 // Raw PRMT (generic mode).  NOT __byte_perm: that intrinsic masks the selector with 0x7777, which costs an
@@ -251,7 +255,7 @@ __device__ __forceinline__ void pk_run(PkState<R> &st, int &s, const int s_end, 
 }
 
 template <int R, int L>
-__global__ void __launch_bounds__(PK_WARPS * 32, PK_MIN_CTAS(R))
+__global__ void __launch_bounds__(pk_warps(L) * 32, PK_MIN_CTAS(R) * PK_WARPS / pk_warps(L))
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
                  int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
@@ -281,8 +285,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const unsigned hmask = L == 32 ? 0xffffffffu : (0xffffu << (16 * half));  // the lanes of my unit
     const int warp = threadIdx.x >> 5;
     const int unit = warp * HALVES + half;
-    const int unit_global = (blockIdx.x * PK_WARPS + warp) * HALVES + half;
-    const int total_units = gridDim.x * PK_WARPS * HALVES;
+    const int unit_global = (blockIdx.x * pk_warps(L) + warp) * HALVES + half;
+    const int total_units = gridDim.x * pk_warps(L) * HALVES;
     const int g = consts->gap;
     // reference mode (score_ref_boundaries, repeats.py:23-43): the two halves of a lane word are the two sg_qe
     // alignments of a locus -- every begin penalised, nothing combined; `table` then holds 64-bit (score, end_query) keys
