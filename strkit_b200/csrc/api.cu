@@ -478,7 +478,7 @@ static int pk_lanes_for_class(int R) {
 static PackedDims pk_dims_for_class(int R, int max_flank, int max_m, int w_max) {
     const int L = pk_lanes_for_class(R);
     PackedDims d;
-    d.colt_entries = max_flank + 64;
+    d.colt_entries = max_flank + 2 * L;  // columns -(L - 1) .. flank + (L - 1), one spare
     d.prof_words = L == 16 ? pk_prof_words(2 * R, max_m, 16) : pk_prof_words(R, max_m, 32);
     d.w_max = w_max;
     return d;
