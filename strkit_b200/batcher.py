@@ -66,37 +66,39 @@ class ReadBatch:
 
 
 def pack_loci(loci: Iterable[LocusReads]) -> ReadBatch:
-    """Pack per-locus string tuples into one arena.  One bytes.join for the sequences; the per-read Python
-    work is only the length bookkeeping (use strkit_b200.synth for fully vectorised synthetic batches)."""
-    chunks: list[bytes] = []
-    lens: list[tuple[int, int, int]] = []
-    est: list[int] = []
-    read_begin = [0]
-    motif_lens: list[int] = []
-    motifs: list[bytes] = []
+    """Pack per-locus string tuples into one arena.  The per-read Python work is kept to list building done by
+    C-level iterators (zip / chain / map): one str.join + one encode for all sequences, lengths through
+    np.fromiter(map(len, ...)).  (strkit_b200.synth builds fully vectorised synthetic batches.)"""
+    from itertools import chain
+
+    loci = list(loci)
+    n_per = []
     for lr in loci:
         n = len(lr.tr_seqs)
         if not (len(lr.est_cn) == len(lr.flank_left_seqs) == len(lr.flank_right_seqs) == n):
             raise ValueError("LocusReads: per-read sequences must have equal lengths")
-        for e, tr, fl, fr in zip(lr.est_cn, lr.tr_seqs, lr.flank_left_seqs, lr.flank_right_seqs):
-            chunks.append(fl.encode("ascii"))
-            chunks.append(tr.encode("ascii"))
-            chunks.append(fr.encode("ascii"))
-            lens.append((len(fl), len(tr), len(fr)))
-            est.append(int(e))
-        read_begin.append(len(est))
-        motifs.append(lr.motif.encode("ascii"))
-        motif_lens.append(len(lr.motif))
-    lens_a = np.asarray(lens, dtype=np.int32).reshape(-1, 3)
+        n_per.append(n)
+    n_reads = sum(n_per)
+    # fl, tr, fr of every read, in read order
+    seqs = list(chain.from_iterable(chain.from_iterable(zip(lr.flank_left_seqs, lr.tr_seqs, lr.flank_right_seqs))
+                                    for lr in loci))
+    lens_a = np.fromiter(map(len, seqs), dtype=np.int32, count=3 * n_reads).reshape(-1, 3)
+    est = np.fromiter(chain.from_iterable(lr.est_cn for lr in loci), dtype=np.int32, count=n_reads)
+    motifs = [lr.motif for lr in loci]
+    motif_len = np.fromiter(map(len, motifs), dtype=np.int32, count=len(motifs))
+    read_begin = np.zeros(len(loci) + 1, dtype=np.int64)
+    np.cumsum(n_per, out=read_begin[1:])
     tot = lens_a.sum(axis=1, dtype=np.int64)
-    seq_off = np.zeros(len(est), dtype=np.uint64)
-    if len(est):
+    seq_off = np.zeros(n_reads, dtype=np.uint64)
+    if n_reads:
         seq_off[1:] = np.cumsum(tot)[:-1]
     seq_bytes = int(tot.sum())
-    motif_len = np.asarray(motif_lens, dtype=np.int32)
-    motif_off = np.zeros(len(motif_lens), dtype=np.uint64)
-    if len(motif_lens):
+    motif_off = np.zeros(len(motifs), dtype=np.uint64)
+    if len(motifs):
         motif_off[:] = seq_bytes + np.concatenate([[0], np.cumsum(motif_len, dtype=np.int64)[:-1]])
-    arena = np.frombuffer(b"".join(chunks) + b"".join(motifs), dtype=np.uint8)
-    return ReadBatch(arena=arena, seq_off=seq_off, lens=lens_a, est_cn=np.asarray(est, dtype=np.int32),
-                     read_begin=np.asarray(read_begin, dtype=np.int64), motif_off=motif_off, motif_len=motif_len)
+    blob = ("".join(seqs) + "".join(motifs)).encode("ascii")
+    if len(blob) != seq_bytes + int(motif_len.sum(dtype=np.int64)):
+        raise ValueError("pack_loci: sequences must be ASCII")
+    arena = np.frombuffer(blob, dtype=np.uint8)
+    return ReadBatch(arena=arena, seq_off=seq_off, lens=lens_a, est_cn=est, read_begin=read_begin, motif_off=motif_off,
+                     motif_len=motif_len)
