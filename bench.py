@@ -329,6 +329,35 @@ def main():
                "blocking_call_value": reduce_sum(float(reads_per_step) * e2e_steps) / dt_call,
                "equals_resident_results": e2e_parity}
 
+    # ---- the reference-genome path of the same loci (get_ref_repeat_count, once per locus; repeats.py:73-192):
+    # the first read of every locus of batch 0 stands in for the reference window
+    ref_path = None
+    if rank == 0:
+        from strkit_b200.batcher import ReadBatch
+
+        hb = host_batches[0]
+        first = hb.read_begin[:-1]
+        lens = hb.lens[first].copy()
+        tot = lens.sum(axis=1).astype(np.int64)
+        r_off = np.concatenate([[0], np.cumsum(tot)[:-1]]).astype(np.int64)
+        src = np.repeat(hb.seq_off[first].astype(np.int64) - r_off, tot) + np.arange(int(tot.sum()))
+        ml = hb.motif_len.astype(np.int64)
+        m_off = int(tot.sum()) + np.concatenate([[0], np.cumsum(ml)[:-1]]).astype(np.int64)
+        msrc = np.repeat(hb.motif_off.astype(np.int64) - m_off, ml) + int(tot.sum()) + np.arange(int(ml.sum()))
+        ref = ReadBatch(arena=np.concatenate([hb.arena[src], hb.arena[msrc]]), seq_off=r_off.astype(np.uint64), lens=lens,
+                        est_cn=hb.est_cn[first].copy(), read_begin=np.arange(hb.n_loci + 1, dtype=np.int64),
+                        motif_off=m_off.astype(np.uint64), motif_len=hb.motif_len)
+        rc = np.tile(np.array([250, 3, 1], dtype=np.int32), (hb.n_loci, 1))  # repeat_count_params.py:25-27
+        start, ref_size = ref.est_cn.copy(), ref.lens[:, 1].copy()
+        eng.ref_counts(ref, start, ref_size, rc, 5)  # grows the recycled device buffers
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.ref_counts(ref, start, ref_size, rc, 5)
+        dt_ref = (time.perf_counter() - t0) / 3
+        ref_path = {"loci_per_s": hb.n_loci / dt_ref, "ms_per_block": dt_ref * 1e3, "loci_per_block": hb.n_loci,
+                    "how": "Engine.ref_counts, host arrays in / 8 ints per locus out, one GPU",
+                    "share_of_read_path_time": dt_ref * 1e3 / (elapsed_ms / max(1, args.steps))}
+
     # ---- parity spot-check + CPU baseline on a bounded sample (rank 0)
     cpu = None
     parity = None
@@ -375,7 +404,7 @@ def main():
                                      f"{peak['alu_pipe']:.2f}, FMA-pipe only: {peak['fma_pipe']:.2f})",
                          "hbm": {"achieved": arena_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "note": "arena streaming only; the path is INT-ALU bound, not HBM bound"}},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(agg["kernel_launches"]),
+            "cpu_baseline": cpu, "e2e": e2e, "ref_path": ref_path, "gpu_launches": int(agg["kernel_launches"]),
             "replay_ms_per_step": agg["replay_ms"] / max(1, args.steps),
             "widening_passes": int(agg["widening_passes"]),
             "reads_packed_kernel": int(agg["reads_packed_kernel"]),
