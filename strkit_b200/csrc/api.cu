@@ -590,6 +590,99 @@ static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
     return STRK_OK;
 }
 
+// The same validation + planning on the host, for small batches (the per-call wrappers of the drop-in API send one
+// read at a time): no planning kernels, no read-backs, no stream synchronisation.  Mirrors plan.cuh rule for rule.
+#define STRK_SMALL_BATCH 512
+static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, const uint64_t *seq_off, const int32_t *lens,
+                           const int32_t *est_cn, const int64_t *read_begin, const uint64_t *motif_off,
+                           const int32_t *motif_len) {
+    const long long n_reads = b->n_reads, n_loci = b->n_loci;
+    cudaStream_t st = ctx->stream;
+    if (n_reads == 0) {
+        CU(cudaStreamSynchronize(st));
+        return STRK_OK;
+    }
+    static const char *what[] = {"", "has a negative length", "is empty (fl + tr + fr has no bases)", "is too long",
+                                 "runs past the end of the arena", "has an out-of-range est_cn", "has an empty motif",
+                                 "has a motif that runs past the end of the arena", "has a non-monotone read_begin"};
+    std::vector<int> read_locus((size_t)n_reads, 0), order((size_t)n_reads);
+    std::vector<unsigned char> bin((size_t)n_reads, 0);
+    unsigned long long first_error = ~0ull;
+    auto report = [&](long long index, int kind) {
+        const unsigned long long key = ((unsigned long long)index << 8) | (unsigned long long)kind;
+        if (key < first_error) first_error = key;
+    };
+    for (long long l = 0; l < n_loci; ++l) {
+        const long long r0 = read_begin[l], r1 = read_begin[l + 1];
+        if (r1 < r0 || r0 < 0 || r1 > n_reads) {
+            report(l, PLAN_ERR_READ_BEGIN);
+            continue;
+        }
+        if (motif_len[l] <= 0)
+            report(l, PLAN_ERR_MOTIF_EMPTY);
+        else if (motif_off[l] + (unsigned long long)motif_len[l] > arena_bytes)
+            report(l, PLAN_ERR_MOTIF_PAST_ARENA);
+        for (long long r = r0; r < r1; ++r) read_locus[(size_t)r] = (int)l;
+    }
+    long long cnt[STRK_PK_NBIN] = {0};
+    if (first_error == ~0ull) {
+        for (long long r = 0; r < n_reads; ++r) {
+            const int fl = lens[3 * r], tr = lens[3 * r + 1], fr = lens[3 * r + 2];
+            const long long n1 = (long long)fl + tr + fr;
+            const int est = est_cn[r];
+            int bb = 0;
+            if (fl < 0 || tr < 0 || fr < 0)
+                report(r, PLAN_ERR_NEG_LEN);
+            else if (n1 <= 0)
+                report(r, PLAN_ERR_EMPTY);
+            else if (n1 > (1 << 24))
+                report(r, PLAN_ERR_TOO_LONG);
+            else if (seq_off[r] + (unsigned long long)n1 > arena_bytes)
+                report(r, PLAN_ERR_PAST_ARENA);
+            else if (est < 0 || est > (1 << 22))
+                report(r, PLAN_ERR_EST);
+            else {
+                const int m = motif_len[read_locus[(size_t)r]];
+                int R = ctx->h_consts.packed_ok ? strk_pick_rows_packed((int)n1 + 1) : 0;
+                if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128 || m <= 0) R = 0;
+                bb = R;
+                b->max_n1 = std::max(b->max_n1, (int)n1);
+                if (bb) {
+                    b->bin_mmax[bb] = std::max(b->bin_mmax[bb], m);
+                    b->bin_flank[bb] = std::max(b->bin_flank[bb], std::max(fl, fr));
+                }
+                if (n1 > 32 * 16 && m > 0) {
+                    b->mb_cols_base = std::max(b->mb_cols_base, std::max(fl, fr) + m * est);
+                    b->mb_m = std::max(b->mb_m, m);
+                }
+            }
+            bin[(size_t)r] = (unsigned char)bb;
+            ++cnt[bb];
+        }
+    }
+    if (first_error != ~0ull) {
+        const long long idx = (long long)(first_error >> 8);
+        const int kind = (int)(first_error & 0xff);
+        return set_err(STRK_ERR_ARG, "batch: %s %lld %s", kind >= PLAN_ERR_MOTIF_EMPTY ? "locus" : "read", idx,
+                       what[kind <= 8 ? kind : 0]);
+    }
+    // segment offsets: general first, then packed classes from R = 16 down to 2 (as batch_plan)
+    long long off[STRK_PK_NBIN], acc = cnt[0];
+    off[0] = 0;
+    b->n_general = cnt[0];
+    for (int k = STRK_PK_RMAX; k >= 1; --k) {
+        off[k] = acc;
+        b->bin_off[k] = acc;
+        b->bin_cnt[k] = cnt[k];
+        acc += cnt[k];
+    }
+    for (long long r = 0; r < n_reads; ++r) order[(size_t)off[bin[(size_t)r]]++] = (int)r;
+    CU(cudaMemcpyAsync(b->d_read_locus, read_locus.data(), (size_t)n_reads * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->d_order, order.data(), (size_t)n_reads * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->bin.p, bin.data(), (size_t)n_reads, cudaMemcpyHostToDevice, st));
+    return STRK_OK;  // pageable sources: the copies above have been staged when the calls return
+}
+
 // H2D into (possibly recycled) device buffers, then validation + work planning on the device (plan.cuh)
 static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                       const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
@@ -635,6 +728,7 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
         return set_err(e == cudaErrorMemoryAllocation ? STRK_ERR_NOMEM : STRK_ERR_CUDA, "batch upload: %s",
                        cudaGetErrorString(e));
     }
+    if (n_reads <= STRK_SMALL_BATCH) return batch_plan_host(ctx, b, arena_bytes, seq_off, lens, est_cn, read_begin, motif_off, motif_len);
     return batch_plan(ctx, b, arena_bytes);
 }
 
@@ -708,6 +802,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
     std::vector<unsigned char> h_status, h_bin;
     std::vector<int> h_class_lists;
     float ms_dp = 0.f, ms_replay = 0.f;
+    double acc[2] = {0, 0};  // [0] reference-equivalent cells, [1] executed cells
 
     for (int pass = 0;; ++pass) {
         if (wd > (STRK_MAX_WINDOW - 1) / 2) wd = (STRK_MAX_WINDOW - 1) / 2;
@@ -807,6 +902,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         CU(cudaEventRecord(ctx->ev[2], st));
         unsigned int miss_fb[2] = {0, 0};  // [0] loci whose search left the window, [1] packed-kernel fallbacks
         CU(cudaMemcpyAsync(miss_fb, ctx->d_queue + 1, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(acc, ctx->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));  // cumulative over passes
         CU(cudaStreamSynchronize(st));
         const unsigned int miss = miss_fb[0];
         if (use_packed) {
@@ -862,8 +958,6 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         d_slot_begin = ctx->list_c.p;
         wd *= 8;
     }
-    double acc[2] = {0, 0};
-    CU(cudaMemcpy(acc, ctx->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost));
     ctx->stats[0] = acc[1];
     ctx->stats[1] = acc[0];
     ctx->stats[3] = ms_dp;

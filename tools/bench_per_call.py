@@ -8,7 +8,9 @@ tr = motif * 30
 strkit_b200.get_repeat_count(30, tr, fl, fr, motif, p)
 t = time.perf_counter()
 for i in range(500):
-    strkit_b200.get_repeat_count(30 + i, tr + motif * i, fl, fr, motif, p)  # distinct tuples: no lru_cache hits
+    # distinct tuples (no lru_cache hits), HiFi-sized: one flank base changes per call
+    f2 = fl[:i % 70] + "ACGT"[(i // 70) % 4] + fl[i % 70 + 1:]
+    strkit_b200.get_repeat_count(30, tr, f2, fr, motif, p)
 dt = (time.perf_counter() - t) / 500
 print("get_repeat_count per call: %.1f us" % (dt * 1e6))
 rp = strkit_b200.get_reference_rc_params("repalign", 30, 250)
