@@ -349,6 +349,8 @@ def main():
                         motif_off=m_off.astype(np.uint64), motif_len=hb.motif_len)
         rc = np.tile(np.array([250, 3, 1], dtype=np.int32), (hb.n_loci, 1))  # repeat_count_params.py:25-27
         start, ref_size = ref.est_cn.copy(), ref.lens[:, 1].copy()
+        for a in (ref.arena, ref.seq_off, ref.lens, ref.motif_off, start, ref_size, rc):  # pinned, like the reads
+            strkit_b200._native.check(strkit_b200._native.lib.strk_host_register(a.ctypes.data, a.nbytes))
         eng.ref_counts(ref, start, ref_size, rc, 5)  # grows the recycled device buffers
         t0 = time.perf_counter()
         for _ in range(3):
