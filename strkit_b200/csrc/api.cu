@@ -130,6 +130,10 @@ struct strk_batch {
     std::vector<long long> h_read_begin;
     DevBuf<unsigned char> bin;
     int max_n1 = 0, mb_cols_base = 0, mb_m = 0;
+    // first-window policy, carried from one block of loci to the next one filled into this object: 1 = short motifs
+    // get the wider first window of strk_read_wd (set when a block sent > 2.5 % of its loci to a second pass,
+    // cleared when < 1 % of a block's loci used the margin).  Speed only: results never depend on the window.
+    int wide_short = 0;
     // work plan over h_order: [0, n_general) general-kernel-only reads, then one segment per packed R
     long long n_general = 0;
     long long bin_off[STRK_PK_NBIN] = {0}, bin_cnt[STRK_PK_NBIN] = {0};  // index R (0 = general kernel)
@@ -793,6 +797,10 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         int v = atoi(env);
         if (v >= 1 && v <= 64) wd = v;
     }
+    static const bool trace = getenv("STRK_RUN_TRACE") != nullptr;
+    int ws = b->wide_short;
+    if (const char *env = getenv("STRK_WIDE_SHORT")) ws = atoi(env) != 0;  // tuning only
+    const int wd_cap = (STRK_MAX_WINDOW - 1) / 2 - 2;
     long long n_slots = b->n_reads;
     long long n_list = b->n_loci;
     const int *d_read_ids = nullptr, *d_locus_ids = nullptr;
@@ -805,18 +813,18 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
     double acc[2] = {0, 0};  // [0] reference-equivalent cells, [1] executed cells
 
     for (int pass = 0;; ++pass) {
-        if (wd > (STRK_MAX_WINDOW - 1) / 2) wd = (STRK_MAX_WINDOW - 1) / 2;
-        const int W = 2 * wd + 1;
+        if (wd > wd_cap) wd = wd_cap;
+        const int W = 2 * strk_read_wd(wd, 1, ws) + 1;  // table stride: the widest per-read window
         if (ctx->fams.reserve((size_t)n_slots) != cudaSuccess || ctx->table.reserve((size_t)n_slots * (size_t)W) != cudaSuccess) {
             cudaGetLastError();
             return set_err(STRK_ERR_NOMEM, "cannot allocate score tables for %lld reads x %d sizes", n_slots, W);
         }
         int b_len, rowlen;
-        scratch_dims(b, wd, &b_len, &rowlen);
+        scratch_dims(b, strk_read_wd(wd, 1, ws), &b_len, &rowlen);
         const int threads = 256;
         plan_reads_kernel<<<(unsigned)((n_slots + threads - 1) / threads), threads, 0, st>>>(
             d_read_ids, n_slots, b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_off, b->d_motif_len, wd,
-            W, ctx->fams.p, ctx->d_acc + 1);
+            ws, W, ctx->fams.p, ctx->d_acc + 1);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[0], st));
@@ -838,6 +846,8 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             }
             const int *seg_list[STRK_PK_NBIN];
             long long seg_cnt[STRK_PK_NBIN];
+            int seg_flank[STRK_PK_NBIN], seg_mmax[STRK_PK_NBIN];
+            for (int k = 0; k < STRK_PK_NBIN; ++k) seg_flank[k] = b->bin_flank[k], seg_mmax[k] = b->bin_mmax[k];
             if (pass == 0) {
                 for (int k = 0; k < STRK_PK_NBIN; ++k) seg_list[k] = b->d_order + b->bin_off[k], seg_cnt[k] = b->bin_cnt[k];
                 seg_cnt[0] = b->n_general;
@@ -849,7 +859,27 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                     CU(cudaStreamSynchronize(st));
                 }
                 std::vector<int> by_class[STRK_PK_NBIN];
-                for (size_t sl = 0; sl < h_read_ids.size(); ++sl) by_class[h_bin[(size_t)h_read_ids[sl]]].push_back((int)sl);
+                // A small pass is launch-latency bound (one read's sweep is ~100 us whatever the grid): its reads run
+                // in the largest class of their lane group (pad rows cost nothing there), two launches instead of 15.
+                int merged[STRK_PK_NBIN];
+                for (int k = 0; k < STRK_PK_NBIN; ++k) merged[k] = k;
+                if (h_read_ids.size() <= 8192) {
+                    bool used[STRK_PK_NBIN] = {false};
+                    for (int r : h_read_ids) used[h_bin[(size_t)r]] = true;
+                    for (int L = 16; L <= 32; L += 16) {
+                        int top = 0;
+                        for (int k = 1; k < STRK_PK_NBIN; ++k)
+                            if (used[k] && pk_lanes_for_class(k) == L) top = k;
+                        for (int k = 1; k < top; ++k)
+                            if (used[k] && pk_lanes_for_class(k) == L) {
+                                merged[k] = top;
+                                seg_flank[top] = seg_flank[top] > seg_flank[k] ? seg_flank[top] : seg_flank[k];
+                                seg_mmax[top] = seg_mmax[top] > seg_mmax[k] ? seg_mmax[top] : seg_mmax[k];
+                            }
+                    }
+                }
+                for (size_t sl = 0; sl < h_read_ids.size(); ++sl)
+                    by_class[merged[h_bin[(size_t)h_read_ids[sl]]]].push_back((int)sl);
                 h_class_lists.clear();
                 size_t at[STRK_PK_NBIN];
                 for (int k = 0; k < STRK_PK_NBIN; ++k) {
@@ -871,7 +901,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             for (int k = STRK_PK_RMAX; k >= 1; --k) {
                 if (!seg_cnt[k]) continue;
                 const int R = k;
-                const PackedDims dims = pk_dims_for_class(R, b->bin_flank[k], b->bin_mmax[k], (W + 3) / 4 * 4);
+                const PackedDims dims = pk_dims_for_class(R, seg_flank[k], seg_mmax[k], (W + 3) / 4 * 4);
                 if (pk_smem_for_class(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
                     rc = launch_general(ctx, false, ctx->fams.p, seg_list[k], seg_cnt[k], b->d_arena, ctx->table.p, b_len,
@@ -893,15 +923,17 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         }
         CU(cudaEventRecord(ctx->ev[1], st));
         CU(cudaMemsetAsync(ctx->d_queue + 1, 0, sizeof(unsigned int), st));
+        CU(cudaMemsetAsync(ctx->d_queue + 3, 0, sizeof(unsigned int), st));
         replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
-            ctx->table.p, W, wd, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
+            ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
             b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
             ctx->d_queue + 1, ctx->d_acc);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[2], st));
-        unsigned int miss_fb[2] = {0, 0};  // [0] loci whose search left the window, [1] packed-kernel fallbacks
-        CU(cudaMemcpyAsync(miss_fb, ctx->d_queue + 1, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        // [0] loci whose search left the window, [1] packed-kernel fallbacks, [2] loci saved by the wide_short margin
+        unsigned int miss_fb[3] = {0, 0, 0};
+        CU(cudaMemcpyAsync(miss_fb, ctx->d_queue + 1, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(acc, ctx->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));  // cumulative over passes
         CU(cudaStreamSynchronize(st));
         const unsigned int miss = miss_fb[0];
@@ -915,11 +947,19 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         ms_dp += t0;
         ms_replay += t1;
         ctx->stats[7] += (double)n_slots;
+        if (trace)
+            fprintf(stderr, "[strk_batch_run %p] pass %d: wd %d (wide_short %d, %d sizes), %lld reads of %lld loci, %s kernel, "
+                    "dp %.3f ms, replay %.3f ms, %u loci left the window, %u used the margin, %u fallbacks\n", (void *)ctx, pass, wd, ws, W,
+                    n_slots, n_list, use_packed ? "packed" : "general", t0, t1, miss, miss_fb[2], miss_fb[1]);
+        if (pass == 0 && b->n_loci >= 256) {  // policy for the next block filled into this batch object
+            if (!ws && (long long)miss * 40 > b->n_loci) b->wide_short = 1;
+            if (ws && (long long)(miss + miss_fb[2]) * 100 < b->n_loci) b->wide_short = 0;
+        }
         if (miss == 0) break;
 
         // widening pass: redo the loci whose search left the window (status 1); status 2 is an error
         ctx->stats[5] += 1;
-        if (wd >= (STRK_MAX_WINDOW - 1) / 2)
+        if (wd >= wd_cap)
             return set_err(STRK_ERR_SEARCH, "search left the widest supported window (%d sizes)", STRK_MAX_WINDOW);
         h_status.resize((size_t)b->n_loci);
         CU(cudaMemcpy(h_status.data(), b->d_status, (size_t)b->n_loci, cudaMemcpyDeviceToHost));
@@ -956,7 +996,9 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         d_read_ids = ctx->list_a.p;
         d_locus_ids = ctx->list_b.p;
         d_slot_begin = ctx->list_c.p;
-        wd *= 8;
+        int widen = pass == 0 ? 4 : 8;  // most second passes need a few more sizes, the rest are far off
+        if (const char *env = getenv("STRK_WIDEN1")) widen = pass == 0 && atoi(env) >= 2 ? atoi(env) : widen;  // tuning only
+        wd *= widen;
     }
     ctx->stats[0] = acc[1];
     ctx->stats[1] = acc[0];

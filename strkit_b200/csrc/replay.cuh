@@ -20,6 +20,7 @@ struct ClimbResult {
     int best_n, best_score, n_explored;
     int status;  // 0 ok, 1 window miss, 2 nothing scored
     double sum_n;  // sum of the sizes scored (for reference-equivalent cell counts)
+    int lo_touched, hi_touched;  // extent of the sizes looked up
 };
 
 struct SeenSet {
@@ -54,6 +55,8 @@ __host__ __device__ inline ClimbResult climb_single(const int *table, int n_lo, 
     res.n_explored = 0;
     res.status = 0;
     res.sum_n = 0.0;
+    res.lo_touched = 0x7fffffff;
+    res.hi_touched = -1;
     seen.reset(n_lo, n_hi);
     int st_size[4], st_dir[4];
     int top = 0;
@@ -69,6 +72,8 @@ __host__ __device__ inline ClimbResult climb_single(const int *table, int n_lo, 
         int start_size = size - ((dir < 1 || wide) ? range : 0);
         if (start_size < 0) start_size = 0;
         const int end_size = size + ((dir > -1 || wide) ? range : 0);
+        res.lo_touched = start_size < res.lo_touched ? start_size : res.lo_touched;
+        res.hi_touched = end_size > res.hi_touched ? end_size : res.hi_touched;
         bool have = false;
         int mv_size = 0, mv_score = 0;
         for (int i = start_size; i <= end_size; ++i) {
@@ -195,10 +200,13 @@ __host__ __device__ inline RefClimbResult climb_ref(const long long *tab, int n_
 }
 
 // One thread per locus: the read loop of call_locus.py:1129-1161 over the score tables.
-//   table row of slot s = table + s * W ; window of the slot = [max(0, est - wd), est + wd]
+//   table row of slot s = table + s * W ; window of the slot = [max(0, est - wdr), est + wdr], wdr = strk_read_wd()
+//   miss_count[0] += loci whose search left the window; miss_count[2] += loci that stayed inside it but went
+//   beyond est +- wd, i.e. that only the wide_short margin saved from a second pass
 //   locus_ids == nullptr: locus q is q and its slots are read_begin[q]..; otherwise the widening
 //   pass lists the loci to redo and slot_begin[q] is the first slot of locus_ids[q].
-__global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd, const int *__restrict__ locus_ids,
+__global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd, int wide_short,
+                                    const int *__restrict__ locus_ids,
                                     const long long *__restrict__ slot_begin, int n_list,
                                     const long long *__restrict__ read_begin, const int *__restrict__ est_cn,
                                     const int *__restrict__ lens, const int *__restrict__ motif_len, int max_iters,
@@ -214,7 +222,9 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
     double frac = 0.0;  // read_offset_frac_from_starting_guess (:1079)
     double cells = 0.0;
     const int m = motif_len[locus];
+    const int wdr = strk_read_wd(wd, m, wide_short);
     int status = 0;
+    bool margin_used = false;
     for (long long r = r0; r < r1; ++r, ++slot) {
         const int est = est_cn[r];
         int read_sc = est;
@@ -223,14 +233,15 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
             frac = 0.0;  // :1133
         else
             read_sc += off;  // :1136
-        const int n_lo = est - wd > 0 ? est - wd : 0;
-        const int n_hi = est + wd;
+        const int n_lo = est - wdr > 0 ? est - wdr : 0;
+        const int n_hi = est + wdr;
         ClimbResult cr =
             climb_single(table + (size_t)slot * (size_t)W, n_lo, n_hi, read_sc, max_iters, range, step, tie_flags, seen);
         if (cr.status) {
             status = cr.status;
             break;
         }
+        margin_used |= cr.lo_touched < est - wd || cr.hi_touched > est + wd;
         out[4 * r + 0] = cr.best_n;
         out[4 * r + 1] = cr.best_score;
         out[4 * r + 2] = cr.n_explored;
@@ -240,10 +251,12 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
         cells += n1 * ((double)cr.n_explored * (double)(lens[3 * r] + lens[3 * r + 2]) + (double)m * cr.sum_n);
     }
     locus_status[locus] = (unsigned char)status;
-    if (status)
+    if (status) {
         atomicAdd(miss_count, 1u);
-    else
+    } else {
         atomicAdd(ref_cells, cells);
+        if (margin_used) atomicAdd(miss_count + 2, 1u);
+    }
 }
 
 // Builds the family descriptors of a pass on the device (no descriptor H2D traffic).
@@ -252,7 +265,7 @@ __global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_
                                   const unsigned long long *__restrict__ seq_off, const int *__restrict__ lens,
                                   const int *__restrict__ est_cn, const int *__restrict__ read_locus,
                                   const unsigned long long *__restrict__ motif_off, const int *__restrict__ motif_len,
-                                  int wd, int W, FamDesc *__restrict__ fams, double *exec_cells) {
+                                  int wd, int wide_short, int W, FamDesc *__restrict__ fams, double *exec_cells) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cells = 0.0;
     if (s < n_slots) {
@@ -267,8 +280,9 @@ __global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_
     f.n_fr = lens[3 * r + 2];
     f.m = motif_len[locus];
     const int est = est_cn[r];
-    f.n_lo = est - wd > 0 ? est - wd : 0;
-    f.n_hi = est + wd;
+    const int wdr = strk_read_wd(wd, f.m, wide_short);
+    f.n_lo = est - wdr > 0 ? est - wdr : 0;
+    f.n_hi = est + wdr;
     fams[s] = f;
     // executed DP cells: one forward sweep over fl + motif*n_hi plus one backward sweep over fr
     cells = (double)(f.n_fl + f.n_tr + f.n_fr) * ((double)f.n_fl + (double)f.m * (double)f.n_hi + (double)f.n_fr);

@@ -42,6 +42,13 @@ struct ScoreConsts {
     unsigned one_v[32];
 };
 
+// Half-width (in copies) of a read's score window.  wide_short = 1 gives short motifs a wider first window: a noisy
+// read's length estimate is off by a few BASES, which is more copies the shorter the motif (ONT-like reads miss a
+// +-6 window at 29 % of the 2-mer loci, 4 % of the 3-mers, 1 % of the 4-mers; none at +-8 / +-8 / +-7).
+__host__ __device__ inline int strk_read_wd(int wd, int m, int wide_short) {
+    return wd + (wide_short ? (m <= 3 ? 2 : (m == 4 ? 1 : 0)) : 0);
+}
+
 // rows per lane of the packed kernel (32*R >= n1, every R in 2..16 is instantiated); 0 = too long for it
 #define STRK_PK_RMAX 16
 #define STRK_PK_NBIN (STRK_PK_RMAX + 1)  // work classes of a batch: [0] general kernel only, [R] packed kernel with R rows per lane
