@@ -83,6 +83,10 @@ struct strk_ctx {
     const void *l2_window_ptr = nullptr;
     size_t l2_window_bytes = 0;
     cudaStream_t l2_window_stream = nullptr;
+    // small passes: one side stream per rows-per-lane class, so the class launches (each under one wave) overlap
+    cudaStream_t side[STRK_PK_NBIN] = {nullptr};
+    cudaEvent_t side_ev[STRK_PK_NBIN] = {nullptr};
+    cudaEvent_t fork_ev = nullptr;
     cudaStream_t stream = nullptr;
     ScoreConsts h_consts;
     ScoreConsts *d_consts = nullptr;
@@ -308,6 +312,11 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     if (ctx->d_bin_off) cudaFree(ctx->d_bin_off);
     for (int k = 0; k < 3; ++k)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < STRK_PK_NBIN; ++k) {
+        if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+        if (ctx->side_ev[k]) cudaEventDestroy(ctx->side_ev[k]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return STRK_OK;
@@ -405,7 +414,10 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
 // ------------------------------------------------------------------------------------------------
 template <int R, int L>
 static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
-                           int *table, PackedDims dims, cudaStream_t st, int ref_mode) {
+                           int *table, PackedDims dims, cudaStream_t st, int ref_mode, size_t *plan_scratch,
+                           long long scratch_off) {
+    // plan_scratch != nullptr: only report the capture scratch (uint4 units) this launch needs.
+    // scratch_off >= 0: the launch uses pk_scratch + scratch_off, reserved by the caller (concurrent class launches).
     constexpr int HALVES = 32 / L;
     size_t smem = pk_smem_bytes(R, dims, L);
     if (const char *env = getenv("STRK_PK_EXTRA_SMEM")) smem += (size_t)atoi(env);  // occupancy experiments only
@@ -428,7 +440,11 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
     const long long need = ((long long)n + pk_warps(L) * HALVES - 1) / (pk_warps(L) * HALVES);
     if (grid > need) grid = need;
     const size_t words = pk_scratch_words_per_unit(R, dims.w_max, L) * (size_t)grid * pk_warps(L) * HALVES;
-    if (ctx->pk_scratch.reserve((words + 3) / 4) != cudaSuccess) {
+    if (plan_scratch) {
+        *plan_scratch = (words + 3) / 4;
+        return STRK_OK;
+    }
+    if (scratch_off < 0 && ctx->pk_scratch.reserve((words + 3) / 4) != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", words * 4);
     }
@@ -440,7 +456,7 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
     {
         const size_t bytes = ctx->pk_scratch.cap * sizeof(uint4);  // the whole buffer: set again only when it moves
         static const bool off = getenv("STRK_L2_WINDOW") == nullptr;
-        if (!off && ctx->l2_persist_max && ctx->l2_window_max &&
+        if (!off && scratch_off < 0 && ctx->l2_persist_max && ctx->l2_window_max &&
             (ctx->l2_window_ptr != ctx->pk_scratch.p || ctx->l2_window_bytes != bytes || ctx->l2_window_stream != st)) {
             const size_t win = bytes < ctx->l2_window_max ? bytes : ctx->l2_window_max;
             const size_t carve = win < ctx->l2_persist_max ? win : ctx->l2_persist_max;
@@ -458,8 +474,8 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
         }
     }
     dp_packed_kernel<R, L><<<(unsigned)grid, pk_warps(L) * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
-                                                                        ctx->pk_scratch.p, ctx->fallback.p,
-                                                                        ctx->d_queue + 2, ref_mode);
+                                                                        ctx->pk_scratch.p + (scratch_off > 0 ? scratch_off : 0),
+                                                                        ctx->fallback.p, ctx->d_queue + 2, ref_mode);
     CU(cudaGetLastError());
     ctx->stats[2] += 1;
     return STRK_OK;
@@ -493,11 +509,12 @@ static size_t pk_smem_for_class(int R, const PackedDims &d) {
 
 // ref_mode: the families are reference windows and `table` holds the 64-bit boundary keys (score_ref_boundaries)
 static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *list, int n, const unsigned char *arena,
-                         int *table, PackedDims dims, cudaStream_t st, int ref_mode = 0) {
+                         int *table, PackedDims dims, cudaStream_t st, int ref_mode = 0, size_t *plan_scratch = nullptr,
+                         long long scratch_off = -1) {
     if (pk_lanes_for_class(R) == 16) {
         switch (R) {
 #define PK_CASE(N) \
-    case N: return launch_packed_r<2 * N, 16>(ctx, fams, list, n, arena, table, dims, st, ref_mode);
+    case N: return launch_packed_r<2 * N, 16>(ctx, fams, list, n, arena, table, dims, st, ref_mode, plan_scratch, scratch_off);
             PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8)
 #undef PK_CASE
             default: break;
@@ -505,7 +522,7 @@ static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *l
     }
     switch (R) {
 #define PK_CASE(N) \
-    case N: return launch_packed_r<N, 32>(ctx, fams, list, n, arena, table, dims, st, ref_mode);
+    case N: return launch_packed_r<N, 32>(ctx, fams, list, n, arena, table, dims, st, ref_mode, plan_scratch, scratch_off);
         PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8) PK_CASE(9) PK_CASE(10) PK_CASE(11)
         PK_CASE(12) PK_CASE(13) PK_CASE(14) PK_CASE(15) PK_CASE(16)
 #undef PK_CASE
@@ -896,12 +913,59 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                 for (int k = 0; k < STRK_PK_NBIN; ++k) seg_list[k] = ctx->list_d.p + at[k], seg_cnt[k] = (long long)by_class[k].size();
             }
             CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
-            // one launch per rows-per-lane class, back to back on the run's stream (spreading the classes over
-            // several streams was measured slower: concurrent grids with different footprints fragment the SMs)
+            // One launch per rows-per-lane class.  Large passes: back to back on the run's stream (spreading the
+            // classes over several streams was measured slower there, -2.8 %: concurrent grids with different
+            // footprints fragment the SMs).  Small passes, where a class is less than a wave of CTAs and each launch
+            // lasts one read's sweep whatever its grid: every class on its own side stream with its own slice of
+            // the capture scratch, so the launches overlap (blocks of a few hundred loci, per-locus calls).
+            static const long long fan_max = [] {
+                const char *e = getenv("STRK_PK_FANOUT_MAX");  // reads per pass up to which the classes overlap
+                return e ? atoll(e) : 131072LL;
+            }();
+            long long fan_off[STRK_PK_NBIN];
+            bool fan_out = false;
+            if (n_slots <= fan_max) {
+                size_t total = 0;
+                int n_classes = 0;
+                for (int k = STRK_PK_RMAX; k >= 1; --k) {
+                    fan_off[k] = -1;
+                    if (!seg_cnt[k]) continue;
+                    const PackedDims dims = pk_dims_for_class(k, seg_flank[k], seg_mmax[k], (W + 3) / 4 * 4);
+                    if (pk_smem_for_class(k, dims) > 200 * 1024) continue;
+                    size_t need = 0;
+                    rc = launch_packed(ctx, k, ctx->fams.p, seg_list[k], (int)seg_cnt[k], b->d_arena, ctx->table.p, dims, st, 0,
+                                       &need);
+                    if (rc) return rc;
+                    fan_off[k] = (long long)total;
+                    total += need;
+                    ++n_classes;
+                }
+                if (n_classes >= 2) {
+                    if (ctx->pk_scratch.reserve(total) != cudaSuccess) {
+                        cudaGetLastError();
+                        return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", total * sizeof(uint4));
+                    }
+                    if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+                    CU(cudaEventRecord(ctx->fork_ev, st));
+                    fan_out = true;
+                }
+            }
             for (int k = STRK_PK_RMAX; k >= 1; --k) {
                 if (!seg_cnt[k]) continue;
                 const int R = k;
                 const PackedDims dims = pk_dims_for_class(R, seg_flank[k], seg_mmax[k], (W + 3) / 4 * 4);
+                if (fan_out && fan_off[k] >= 0) {
+                    if (!ctx->side[k]) CU(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+                    if (!ctx->side_ev[k]) CU(cudaEventCreateWithFlags(&ctx->side_ev[k], cudaEventDisableTiming));
+                    CU(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev, 0));
+                    rc = launch_packed(ctx, R, ctx->fams.p, seg_list[k], (int)seg_cnt[k], b->d_arena, ctx->table.p, dims,
+                                       ctx->side[k], 0, nullptr, fan_off[k]);
+                    if (rc) return rc;
+                    CU(cudaEventRecord(ctx->side_ev[k], ctx->side[k]));
+                    CU(cudaStreamWaitEvent(st, ctx->side_ev[k], 0));
+                    n_packed += seg_cnt[k];
+                    continue;
+                }
                 if (pk_smem_for_class(R, dims) > 200 * 1024) {
                     // shared memory would not fit: hand the whole segment to the general kernel
                     rc = launch_general(ctx, false, ctx->fams.p, seg_list[k], seg_cnt[k], b->d_arena, ctx->table.p, b_len,

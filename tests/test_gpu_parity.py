@@ -174,6 +174,31 @@ def test_batch_noisy_ont_and_bad_estimates_force_widening(sb, oracle):
     assert eng.stats()["widening_passes"] >= 1
 
 
+def test_first_window_policy_changes_passes_not_results(sb, oracle, monkeypatch):
+    """Noisy reads switch the blocks that follow to the wider first window for short motifs (strk_read_wd) and the
+    small second passes run merged in the largest class of their lane group: same rows as the oracle whichever
+    window a block was scored with -- policy learnt (2nd call), forced on, forced off, 8x first widening."""
+    from strkit_b200 import synth
+
+    batch = synth.generate(synth.CONFIGS[3], 512, seed=77).to_host()
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                batch.motif_off, batch.motif_len, n_threads=8)
+    eng = sb.Engine()
+    got = eng.count_reads(batch, params)
+    assert np.array_equal(got, want)
+    assert eng.stats()["widening_passes"] >= 1          # +-6 copies: some 2-mer loci leave the window
+    first_pass_reads = eng.stats()["reads_packed_kernel"] + eng.stats()["reads_general_kernel"]
+    got = eng.count_reads(batch, params)                # same batch object: the policy is on now
+    assert np.array_equal(got, want)
+    assert eng.stats()["reads_packed_kernel"] + eng.stats()["reads_general_kernel"] < first_pass_reads
+    for env in ({"STRK_WIDE_SHORT": "1"}, {"STRK_WIDE_SHORT": "0"}, {"STRK_WIDE_SHORT": "0", "STRK_WIDEN1": "8"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        assert np.array_equal(eng.count_reads(batch, params), want), env
+    eng.close()
+
+
 @pytest.mark.parametrize("params", [(7, 3, 1), (50, 3, 2), (50, 1, 4), (200, 3, 3), (0, 3, 1)])
 def test_batch_search_parameters(sb, oracle, params):
     from strkit_b200 import synth
