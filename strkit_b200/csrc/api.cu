@@ -369,12 +369,15 @@ static int validate_motifs(const char *who, uint64_t arena_bytes, const uint64_t
 // ------------------------------------------------------------------------------------------------
 // general DP launch
 // ------------------------------------------------------------------------------------------------
-static const int GEN_THREADS = 256;
+// One warp per CTA: the work queue hands the most expensive families out first, and warps that share a CTA share an
+// SM -- with 8-warp CTAs the eight longest reads of a pass (the ones that bound its duration) competed for one SM's
+// issue slots while most SMs idled.
+static const int GEN_THREADS = 32;
 
 static int general_grid(strk_ctx *ctx, long long n_fams) {
     long long warps_needed = n_fams;
     long long blocks = (warps_needed + (GEN_THREADS / 32) - 1) / (GEN_THREADS / 32);
-    long long cap = (long long)ctx->n_sm * 4;  // persistent: up to 4 CTAs of 8 warps per SM
+    long long cap = (long long)ctx->n_sm * 16;  // persistent: up to 16 one-warp CTAs per SM (128 registers per thread)
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
@@ -386,7 +389,7 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
                           const unsigned int *d_count = nullptr) {
     // d_count != nullptr: the list length lives on the device; n_fams is only its upper bound
     if (n_fams <= 0) return STRK_OK;
-    if (d_count && n_fams > (long long)ctx->n_sm * (GEN_THREADS / 32)) n_fams = (long long)ctx->n_sm * (GEN_THREADS / 32);
+    if (d_count && n_fams > (long long)ctx->n_sm * 4) n_fams = (long long)ctx->n_sm * 4;
     if (n_fams > 0x7fffffffLL) return set_err(STRK_ERR_ARG, "too many families in one launch");
     const int grid = general_grid(ctx, n_fams);
     const size_t per_warp = (size_t)b_len + 2 * (size_t)rowlen;
@@ -988,10 +991,16 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         CU(cudaEventRecord(ctx->ev[1], st));
         CU(cudaMemsetAsync(ctx->d_queue + 1, 0, sizeof(unsigned int), st));
         CU(cudaMemsetAsync(ctx->d_queue + 3, 0, sizeof(unsigned int), st));
-        replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
-            ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
-            b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
-            ctx->d_queue + 1, ctx->d_acc);
+        if (W <= REPLAY_WMAX)
+            replay_reads_small_kernel<<<(unsigned)((n_list + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, 0, st>>>(
+                ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
+                b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
+                ctx->d_queue + 1, ctx->d_acc);
+        else
+            replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
+                ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
+                b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
+                ctx->d_queue + 1, ctx->d_acc);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[2], st));

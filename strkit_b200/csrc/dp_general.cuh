@@ -15,12 +15,12 @@
 // where B is one backward sweep of reverse(fr) against reverse(db).  Max-plus path
 // decomposition: exact, not a heuristic.
 //
-// Rows are FRONT-padded to a multiple of 32*R with a pad symbol whose score reproduces the
-// border row (0 everywhere when the top border is free, -g*j otherwise), so the last real row is
+// Rows are FRONT-padded to a multiple of 32*R with copy rows (see dp_pass), so the last real row is
 // always the last register of lane 31 and the init row needs no special case.
 //
 // Linear gaps only: the reference passes open = extend = 5 (repeats.py:33,40), so parasail's
-// affine recurrence collapses to H = max(diag + s, max(up, left) - g).
+// affine recurrence collapses to H = max(diag + s, max(up, left) - g), evaluated on biased cells
+// H' = H + g * (row + column) as H' = max3(diag' + (s + 2g), up', left') (dp_pass).
 #pragma once
 #include "strk_common.cuh"
 
@@ -61,14 +61,41 @@ __device__ __forceinline__ int border_col0(const PassCfg &c, int i, int g) {
 }
 __device__ __forceinline__ int border_row0(const PassCfg &c, int j, int g) { return c.s2_beg_free ? 0 : -g * j; }
 
-template <int R>
-__device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
+// Scoring tables of the general kernel in shared memory.  Cells are held BIASED: cell (I, j) of the padded matrix
+// stores H + g * (I + j), which turns the linear-gap recurrence into  H' = max3(diag' + (s + 2g), up', left')  --
+// one add and one three-input max per cell, and a dependency chain of one max per row down a lane's strip.
+struct GenSmem {
+    unsigned char lut[256];
+    short smat2[STRK_SMAT_ROWS * STRK_NSYM_];  // [row symbol or pad][column symbol], score + 2g
+    unsigned long long t8[STRK_NSYM_];         // PRMT byte table per column symbol: byte c = score(row class c) + 2g
+    unsigned char cls[STRK_SMAT_ROWS + 1];     // row symbol -> PRMT class (A C G T N X other pad), 0x80 = none
+    unsigned one;                              // = 1, opaque to the compiler: multiplier of the FMA-pipe adds
+};
+
+__device__ __forceinline__ int gen_add(int a, int b, unsigned one) {  // a + b as IMAD (FMA pipe)
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"((int)one), "r"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned gen_prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// One sweep.  LUT = true: every row symbol of the family is A/C/G/T/N/X/other (or pad) and the score of a cell is a
+// PRMT byte select from the column's 8-byte table (PRMT + IMAD + VIMNMX3 per cell); LUT = false (IUPAC codes inside
+// the read): a shared-memory look-up per cell.
+// Pad rows (front padding) are COPY rows: their score entry is 0 (= -2g + 2g), so with up' >= diag' and
+// up' >= left' each one repeats the value above it; lane 0 of the first strip injects DP row 0 biased as the last
+// pad row (index off), which is what the first real row then reads as its up / diagonal neighbour.
+template <int R, bool LUT>
+__device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
     const int lane = threadIdx.x & 31;
     const int RB = 32 * R;
     const int NB = c.n1 <= RB ? 1 : (c.n1 + RB - 1) / RB;
     const int off = NB * RB - c.n1;  // number of pad rows in front
-    const int padcode = c.s2_beg_free ? STRK_PAD_FREE : STRK_PAD_PEN;
-    const int W = c.n_hi - c.n_lo + 1;
+    const unsigned one = sc.one;
 
     if (c.kind == PASS_DUMP && c.ncols == 0) {  // no columns: the last column is the border
         for (int i = lane; i <= c.n1; i += 32) c.B[i] = border_col0(c, i, g);
@@ -90,61 +117,89 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
     }
 
     for (int b = 0; b < NB; ++b) {
-        const int Ibase = b * RB + lane * R;  // padded row index of the row above my strip
-        int sym[R], H[R];
+        const int Ibase = b * RB + lane * R;  // padded index of the row above my strip
+        int H[R];
+        unsigned sel[R];  // LUT: PRMT selector; else: row offset into smat2
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int i = Ibase + r + 1 - off;  // real row 1..n1, <= 0 for pad rows
-            int code = padcode;
-            if (i >= 1) {
-                int idx = c.rev_s1 ? c.n1 - i : i - 1;
-                code = sc.lut[c.s1[idx]];
-            }
-            sym[r] = code * STRK_NSYM_;
-            H[r] = border_col0(c, i, g);
+            const int I = Ibase + r + 1, i = I - off;  // real row 1..n1, <= 0 for pad rows
+            int code = STRK_PAD_PEN;
+            if (i >= 1) code = sc.lut[c.s1[c.rev_s1 ? c.n1 - i : i - 1]];
+            sel[r] = LUT ? ((unsigned)(sc.cls[code] & 7u) | 0x8880u) : (unsigned)(code * STRK_NSYM_);
+            H[r] = i >= 1 ? border_col0(c, i, g) + g * I : g * off;
         }
-        int prev_up = border_col0(c, Ibase - off, g);  // H[row above][0]
+        int prev_up = Ibase - off >= 1 ? border_col0(c, Ibase - off, g) + g * Ibase : g * off;  // row above, column 0
         const int *top = b == 0 ? nullptr : ((b - 1) & 1 ? c.row1 : c.row0);
         int *bot = b < NB - 1 ? (b & 1 ? c.row1 : c.row0) : nullptr;
-        int top_next = 0;
-        if (lane == 0 && top) top_next = top[1];
-        int kk = -1, ncop = 0;
-        int pmax = STRK_NEG_INF;  // running max of the last row (lane 31, last pass)
+        // boundary row of the strip above: fetched 32 columns at a time (one coalesced load per 32 steps, issued 32
+        // steps before its first use) and handed to lane 0 by shuffle -- a per-step load by lane 0 would put an L2
+        // round trip on every step of a multi-strip read
+        int top_cur = 0, top_nxt = 0;
+        if (top && 1 + lane <= c.ncols) top_nxt = top[1 + lane];
+        int pmax = STRK_NEG_INF;  // running max of (last row - g * j): lane 31 of the last strip
+        int ncop = 0;
+        // the column one step ahead: its symbol (and byte table) is fetched while the current column is computed
+        int kk_cur = -1, kk_nxt = -1;
+        unsigned long long t_nxt = 0ull;
+        int code_nxt = 0;
+        auto fetch = [&](int jn) {
+            if (jn < 1 || jn > c.ncols) return;
+            if (jn <= c.n_pre) {
+                code_nxt = sc.lut[c.pre[c.rev_pre ? c.n_pre - jn : jn - 1]];
+            } else {
+                kk_nxt = kk_nxt + 1 == c.m ? 0 : kk_nxt + 1;
+                code_nxt = sc.lut[c.motif[c.rev_motif ? c.m - 1 - kk_nxt : kk_nxt]];
+            }
+            if (LUT) t_nxt = sc.t8[code_nxt];
+        };
+        fetch(1 - lane);
+        const int row0_bias = g * off;
         const int nsteps = c.ncols + 31;
         for (int s = 0; s < nsteps; ++s) {
             const int j = s - lane + 1;
             int up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
             const bool active = j >= 1 && j <= c.ncols;
-            if (lane == 0) {
-                if (top) {
-                    up_in = top_next;
-                    if (j + 1 <= c.ncols) top_next = top[j + 1];
-                } else {
-                    up_in = border_row0(c, j, g);
+            if (top) {
+                if ((s & 31) == 0) {
+                    top_cur = top_nxt;
+                    if (s + 33 + lane <= c.ncols) top_nxt = top[s + 33 + lane];
                 }
+                const int t0 = __shfl_sync(0xffffffffu, top_cur, s & 31);  // top[s + 1]: lane 0 is at column s + 1
+                if (lane == 0) up_in = t0;
+            } else if (lane == 0) {
+                up_in = border_row0(c, j, g) + row0_bias + g * j;  // DP row 0, biased as row `off`
             }
+            const unsigned long long t_cur = t_nxt;
+            const int code_cur = code_nxt;
+            kk_cur = kk_nxt;
+            fetch(j + 1);
             if (!active) continue;
-            // column symbol
-            int colsym;
-            if (j <= c.n_pre) {
-                colsym = sc.lut[c.pre[c.rev_pre ? c.n_pre - j : j - 1]];
-            } else {
-                kk = kk + 1 == c.m ? 0 : kk + 1;
-                colsym = sc.lut[c.motif[c.rev_motif ? c.m - 1 - kk : kk]];
-            }
-            const signed char *srow = sc.smat + colsym;
             int d = prev_up, u = up_in;
             prev_up = up_in;
+            if (LUT) {
+                const unsigned tlo = (unsigned)t_cur, thi = (unsigned)(t_cur >> 32);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                int left = H[r];
-                int h = max(d + (int)srow[sym[r]], max(u, left) - g);
-                d = left;
-                u = h;
-                H[r] = h;
+                for (int r = 0; r < R; ++r) {
+                    const int left = H[r];
+                    const int t = gen_add(d, (int)gen_prmt(tlo, thi, sel[r]), one);
+                    const int h = max(max(t, u), left);
+                    d = left;
+                    u = h;
+                    H[r] = h;
+                }
+            } else {
+                const short *srow = sc.smat2 + code_cur;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int left = H[r];
+                    const int h = max(max(d + (int)srow[sel[r]], u), left);
+                    d = left;
+                    u = h;
+                    H[r] = h;
+                }
             }
             if (bot && lane == 31) bot[j] = H[R - 1];
-            pmax = max(pmax, H[R - 1]);
+            pmax = max(pmax, H[R - 1] - g * j);
 
             // candidate column?
             int n = -1;
@@ -152,27 +207,29 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
                 if (j == c.ncols) n = 0;
             } else if (j == c.n_pre) {
                 n = 0;
-            } else if (j > c.n_pre && kk == c.m - 1) {
+            } else if (j > c.n_pre && kk_cur == c.m - 1) {
                 n = ++ncop;
             }
             if (n < 0) continue;
+            const int bias1 = g * (Ibase + 1 + j);  // bias of my first row at this column
             if (c.kind == PASS_DUMP) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     int i = Ibase + r + 1 - off;
-                    if (i >= 0) c.B[i] = H[r];
+                    if (i >= 0) c.B[i] = H[r] - bias1 - g * r;
                 }
                 if (off == 0 && b == 0 && lane == 0) c.B[0] = border_row0(c, j, g);
             } else if (n >= c.n_lo && n <= c.n_hi) {
+                const int pmax_unb = pmax - g * (NB * RB);  // meaningful on lane 31 of the last strip
                 if (c.kind == PASS_COMBINE) {
                     int best = STRK_NEG_INF;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         int i = Ibase + r + 1 - off;
-                        if (i >= 0) best = max(best, H[r] + c.B[c.n1 - i]);
+                        if (i >= 0) best = max(best, H[r] - bias1 - g * r + c.B[c.n1 - i]);
                     }
                     if (off == 0 && b == 0 && lane == 0) best = max(best, border_row0(c, j, g) + c.B[c.n1]);
-                    if (c.lastrow_term && b == NB - 1 && lane == 31) best = max(best, pmax);
+                    if (c.lastrow_term && b == NB - 1 && lane == 31) best = max(best, pmax_unb);
                     // free s2 begin: a path may start on the top border to the right of this column
                     if (c.s2_beg_free && b == NB - 1 && lane == 31) best = max(best, c.B[c.n1 + 1]);
                     atomicMax(&c.out[n - c.n_lo], best);
@@ -182,7 +239,7 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
                     for (int r = 0; r < R; ++r) {
                         int i = Ibase + r + 1 - off;
                         if (i >= 1) {
-                            long long key = ((long long)H[r] << 32) | (unsigned)(0x7fffffff - i);
+                            long long key = ((long long)(H[r] - bias1 - g * r) << 32) | (unsigned)(0x7fffffff - i);
                             best = key > best ? key : best;
                         }
                     }
@@ -192,10 +249,17 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
         }
         // backward sweep: best value anywhere on its last row (= forward row 0, i.e. paths that skip the
         // whole prefix through a free s2 begin), including the border cell
-        if (c.kind == PASS_DUMP && b == NB - 1 && lane == 31) c.B[c.n1 + 1] = max(pmax, border_col0(c, c.n1, g));
+        if (c.kind == PASS_DUMP && b == NB - 1 && lane == 31)
+            c.B[c.n1 + 1] = max(pmax - g * (NB * RB), border_col0(c, c.n1, g));
         __syncwarp();  // boundary row written by lane 31 is read by lane 0 in the next pass
     }
-    (void)W;
+}
+
+// true when every symbol of the family's db has a PRMT row class (no IUPAC code inside the read)
+__device__ inline bool rows_have_classes(const unsigned char *s1, int n1, const GenSmem &sc) {
+    bool ok = true;
+    for (int i = threadIdx.x & 31; i < n1; i += 32) ok = ok && !(sc.cls[sc.lut[s1[i]]] & 0x80);
+    return __all_sync(0xffffffffu, ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -203,7 +267,7 @@ __device__ void dp_pass(const PassCfg &c, const SmemConsts &sc, int g) {
 // fl + motif*n_hi vs db combines at every candidate column.  `flags` = STRK_*_FREE end flags.
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__device__ void process_read_family(const FamDesc &f, const unsigned char *arena, const SmemConsts &sc, int g,
+__device__ void process_read_family(const FamDesc &f, const unsigned char *arena, const GenSmem &sc, int g,
                                     int flags, int *table, int *scratch, int scratch_rowlen, int scratch_b_len) {
     const int lane = threadIdx.x & 31;
     const int n1 = f.n_fl + f.n_tr + f.n_fr;
@@ -212,6 +276,7 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
     for (int k = lane; k < W; k += 32) out[k] = STRK_NEG_INF;
     __syncwarp();
 
+    const bool lut_ok = rows_have_classes(arena + f.db_off, n1, sc);
     PassCfg c;
     c.s1 = arena + f.db_off;
     c.n1 = n1;
@@ -237,7 +302,10 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
     c.s2_beg_free = (flags & 8) != 0;
     c.kind = PASS_DUMP;
     c.lastrow_term = 0;
-    dp_pass<R>(c, sc, g);
+    if (lut_ok)
+        dp_pass<R, true>(c, sc, g);
+    else
+        dp_pass<R, false>(c, sc, g);
     __syncwarp();
 
     // forward sweep
@@ -251,7 +319,10 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
     c.s2_beg_free = (flags & 4) != 0;
     c.kind = PASS_COMBINE;
     c.lastrow_term = (flags & 8) != 0;
-    dp_pass<R>(c, sc, g);
+    if (lut_ok)
+        dp_pass<R, true>(c, sc, g);
+    else
+        dp_pass<R, false>(c, sc, g);
     __syncwarp();
 }
 
@@ -261,7 +332,7 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
 //   rev: columns reverse(fr) + reverse(motif)*n   rows reverse(db)   -> out64[2*k + 1]
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__device__ void process_ref_family(const FamDesc &f, const unsigned char *arena, const SmemConsts &sc, int g,
+__device__ void process_ref_family(const FamDesc &f, const unsigned char *arena, const GenSmem &sc, int g,
                                    long long *table, int *scratch, int scratch_rowlen, int scratch_b_len) {
     const int lane = threadIdx.x & 31;
     const int n1 = f.n_fl + f.n_tr + f.n_fr;
@@ -270,6 +341,7 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     for (int k = lane; k < 2 * W; k += 32) out[k] = (long long)0x8000000000000000ull;
     __syncwarp();
 
+    const bool lut_ok = rows_have_classes(arena + f.db_off, n1, sc);
     PassCfg c;
     c.s1 = arena + f.db_off;
     c.n1 = n1;
@@ -294,7 +366,10 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     c.rev_motif = 0;
     c.ncols = f.n_fl + f.m * f.n_hi;
     c.out64 = out;
-    dp_pass<R>(c, sc, g);
+    if (lut_ok)
+        dp_pass<R, true>(c, sc, g);
+    else
+        dp_pass<R, false>(c, sc, g);
     __syncwarp();
 
     c.pre = arena + f.db_off + f.n_fl + f.n_tr;
@@ -304,24 +379,31 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     c.rev_motif = 1;
     c.ncols = f.n_fr + f.m * f.n_hi;
     c.out64 = out + W;
-    dp_pass<R>(c, sc, g);
+    if (lut_ok)
+        dp_pass<R, true>(c, sc, g);
+    else
+        dp_pass<R, false>(c, sc, g);
     __syncwarp();
 }
 
 // Persistent kernel: warps pull families from a cost-sorted queue.
 template <bool REF>
-__global__ void __launch_bounds__(256) dp_general_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ order,
+__global__ void __launch_bounds__(32, 16) dp_general_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ order,
                                                          int n_fams, const unsigned char *__restrict__ arena,
                                                          const ScoreConsts *__restrict__ consts, void *table,
                                                          int *scratch, int scratch_rowlen, int scratch_b_len,
                                                          unsigned int *queue,
                                                          const unsigned int *__restrict__ n_fams_dev) {
     if (n_fams_dev) n_fams = (int)*n_fams_dev;  // list length produced on the device (packed-kernel fallbacks)
-    __shared__ SmemConsts sc;
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) sc.lut[k] = consts->lut[k];
-    for (int k = threadIdx.x; k < STRK_SMAT_ROWS * STRK_NSYM_; k += blockDim.x) sc.smat[k] = consts->smat[k];
-    __syncthreads();
+    __shared__ GenSmem sc;
     const int g = consts->gap;
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) sc.lut[k] = consts->lut[k];
+    for (int k = threadIdx.x; k < STRK_SMAT_ROWS * STRK_NSYM_; k += blockDim.x) sc.smat2[k] = (short)(consts->smat[k] + 2 * g);
+    for (int k = threadIdx.x; k < STRK_NSYM_; k += blockDim.x) sc.t8[k] = consts->t8f[k];
+    // (a matrix whose biased scores do not fit a positive byte has no byte tables: every family takes the look-up path)
+    for (int k = threadIdx.x; k <= STRK_SMAT_ROWS; k += blockDim.x) sc.cls[k] = consts->packed_ok ? consts->cls_of[k] : 0x80;
+    if (threadIdx.x == 0) sc.one = consts->one_v[0];
+    __syncthreads();
     const int flags = consts->end_flags;
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
