@@ -369,21 +369,18 @@ static int validate_motifs(const char *who, uint64_t arena_bytes, const uint64_t
 // ------------------------------------------------------------------------------------------------
 // general DP launch
 // ------------------------------------------------------------------------------------------------
-// One warp per CTA: the work queue hands the most expensive families out first, and warps that share a CTA share an
-// SM -- with 8-warp CTAs the eight longest reads of a pass (the ones that bound its duration) competed for one SM's
-// issue slots while most SMs idled.
-static const int GEN_THREADS = 32;
+// One family per CTA of GEN_WARPS warps (dp_general.cuh): the strips of a long read run as a pipeline over the warps.
+static const int GEN_THREADS = GEN_WARPS * 32;
 
 static int general_grid(strk_ctx *ctx, long long n_fams) {
-    long long warps_needed = n_fams;
-    long long blocks = (warps_needed + (GEN_THREADS / 32) - 1) / (GEN_THREADS / 32);
-    long long cap = (long long)ctx->n_sm * 16;  // persistent: up to 16 one-warp CTAs per SM (128 registers per thread)
+    long long blocks = n_fams;
+    long long cap = (long long)ctx->n_sm * (16 / GEN_WARPS);  // persistent: 16 warps per SM (128 registers per thread)
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
 }
 
-// scratch: per warp [b_len ints][rowlen ints][rowlen ints]
+// scratch: per CTA [b_len ints][GEN_RING rows of rowlen ints]
 static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const int *d_order, long long n_fams,
                           const unsigned char *d_arena, void *d_table, int b_len, int rowlen, cudaStream_t st,
                           const unsigned int *d_count = nullptr) {
@@ -392,8 +389,8 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
     if (d_count && n_fams > (long long)ctx->n_sm * 4) n_fams = (long long)ctx->n_sm * 4;
     if (n_fams > 0x7fffffffLL) return set_err(STRK_ERR_ARG, "too many families in one launch");
     const int grid = general_grid(ctx, n_fams);
-    const size_t per_warp = (size_t)b_len + 2 * (size_t)rowlen;
-    const size_t total = per_warp * (size_t)grid * (GEN_THREADS / 32);
+    const size_t per_cta = (size_t)b_len + (size_t)GEN_RING * (size_t)rowlen;
+    const size_t total = per_cta * (size_t)grid;
     if (ctx->scratch.reserve(total) != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of DP scratch", total * sizeof(int));

@@ -1,11 +1,11 @@
 // dp_general.cuh -- general semi-global DP kernel (int32 lanes, any length, any alphabet).
 //
-// One warp per alignment family.  The rows of the DP matrix (db = fl + tr + fr, the sequence the
+// One CTA of GEN_WARPS warps per alignment family.  The rows of the DP matrix (db = fl + tr + fr, the sequence the
 // reference profiles, repeats.py:91-93) are cut into strips: lane t owns R consecutive rows, the
 // warp sweeps the columns (the candidate) as a skewed wavefront -- at step s lane t computes
 // column s - t + 1 -- and the bottom cell of lane t-1 reaches lane t through __shfl_up_sync.
-// Families longer than 32*R rows take several passes; the boundary row travels through a per-warp
-// scratch row in global memory (L2-resident).
+// Families longer than 32*R rows take several strips, pipelined over the warps of the CTA (see GenSync); the boundary
+// row between two strips travels through a ring of scratch rows in global memory (L2-resident).
 //
 // The candidate fl + motif*n + fr is never materialised (reference builds it with
 // f"{fl}{motif * i}{fr}"): columns are generated on the fly from the left flank and the motif
@@ -45,7 +45,20 @@ struct PassCfg {
                           // starts inside the suffix columns (free s2 begin), see dp_pass
     int *out;             // COMBINE: [n_hi - n_lo + 1], pre-set to STRK_NEG_INF
     long long *out64;     // ARGMAX: packed (score << 32 | 0x7fffffff - row), pre-set to LLONG_MIN
-    int *row0, *row1;     // boundary-row scratch, ncols + 1 ints each (multi-pass families only)
+    int *rows;            // boundary-row scratch: GEN_RING rows of rowlen ints (multi-strip families only)
+    int rowlen;
+};
+
+// A family is swept by the GEN_WARPS warps of one CTA: warp w takes the strips w, w + GEN_WARPS, ... and the strips
+// run as a pipeline -- strip b + 1 follows strip b about 64 columns behind, reading the boundary row strip b leaves
+// in the ring slot b % GEN_RING.  A long read (config 4: 12 strips of 6 200 columns) is bound by the latency of its
+// own dependency chain, so four strips in flight cut its time almost four-fold.  progress[slot] = b * stride + last
+// column written: values only grow over the strips that reuse a slot, so a stale value never satisfies a waiter.
+#define GEN_WARPS 4
+#define GEN_RING (GEN_WARPS + 1)
+struct GenSync {
+    volatile long long progress[GEN_RING];
+    unsigned int q;
 };
 
 struct SmemConsts {
@@ -90,21 +103,26 @@ __device__ __forceinline__ unsigned gen_prmt(unsigned a, unsigned b, unsigned se
 // up' >= left' each one repeats the value above it; lane 0 of the first strip injects DP row 0 biased as the last
 // pad row (index off), which is what the first real row then reads as its up / diagonal neighbour.
 template <int R, bool LUT>
-__device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
+__device__ void dp_pass(const PassCfg &c, const GenSmem &sc, GenSync &sy, int g) {
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();  // the previous sweep of this family is complete (its B column, its boundary rows)
+    if (threadIdx.x < GEN_RING) sy.progress[threadIdx.x] = -1;
+    __syncthreads();
     const int RB = 32 * R;
     const int NB = c.n1 <= RB ? 1 : (c.n1 + RB - 1) / RB;
     const int off = NB * RB - c.n1;  // number of pad rows in front
     const unsigned one = sc.one;
 
     if (c.kind == PASS_DUMP && c.ncols == 0) {  // no columns: the last column is the border
-        for (int i = lane; i <= c.n1; i += 32) c.B[i] = border_col0(c, i, g);
-        if (lane == 0) c.B[c.n1 + 1] = border_col0(c, c.n1, g);
-        __syncwarp();
+        if (warp == 0) {
+            for (int i = lane; i <= c.n1; i += 32) c.B[i] = border_col0(c, i, g);
+            if (lane == 0) c.B[c.n1 + 1] = border_col0(c, c.n1, g);
+        }
         return;
     }
     // candidate column 0 (empty left flank and n = 0): scores come from the border column
-    if (c.kind == PASS_COMBINE && c.n_pre == 0 && c.n_lo == 0) {
+    if (warp == 0 && c.kind == PASS_COMBINE && c.n_pre == 0 && c.n_lo == 0) {
         int best = STRK_NEG_INF;
         for (int i = lane; i <= c.n1; i += 32) {
             int b = c.B[c.n1 - i];
@@ -116,7 +134,8 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
         atomicMax(&c.out[0], best);
     }
 
-    for (int b = 0; b < NB; ++b) {
+    const long long stride = (long long)c.ncols + 2;
+    for (int b = warp; b < NB; b += GEN_WARPS) {
         const int Ibase = b * RB + lane * R;  // padded index of the row above my strip
         int H[R];
         unsigned sel[R];  // LUT: PRMT selector; else: row offset into smat2
@@ -129,13 +148,25 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
             H[r] = i >= 1 ? border_col0(c, i, g) + g * I : g * off;
         }
         int prev_up = Ibase - off >= 1 ? border_col0(c, Ibase - off, g) + g * Ibase : g * off;  // row above, column 0
-        const int *top = b == 0 ? nullptr : ((b - 1) & 1 ? c.row1 : c.row0);
-        int *bot = b < NB - 1 ? (b & 1 ? c.row1 : c.row0) : nullptr;
+        // (a sweep without columns computes no cell: nothing is published, nothing may be waited for)
+        const int *top = b == 0 || c.ncols == 0 ? nullptr : c.rows + (size_t)((b - 1) % GEN_RING) * c.rowlen;
+        int *bot = b < NB - 1 ? c.rows + (size_t)(b % GEN_RING) * c.rowlen : nullptr;
+        volatile long long *prog_in = &sy.progress[(b + GEN_RING - 1) % GEN_RING];
+        volatile long long *prog_out = &sy.progress[b % GEN_RING];
+        // wait until the strip above has published its boundary row up to column `col` (clipped to the last one)
+        auto wait_top = [&](int col) {
+            const long long need = (long long)(b - 1) * stride + (col < c.ncols ? col : c.ncols);
+            while (*prog_in < need) __nanosleep(40);
+            __threadfence_block();
+        };
         // boundary row of the strip above: fetched 32 columns at a time (one coalesced load per 32 steps, issued 32
         // steps before its first use) and handed to lane 0 by shuffle -- a per-step load by lane 0 would put an L2
         // round trip on every step of a multi-strip read
         int top_cur = 0, top_nxt = 0;
-        if (top && 1 + lane <= c.ncols) top_nxt = top[1 + lane];
+        if (top) {
+            wait_top(32);
+            if (1 + lane <= c.ncols) top_nxt = __ldcg(top + 1 + lane);
+        }
         int pmax = STRK_NEG_INF;  // running max of (last row - g * j): lane 31 of the last strip
         int ncop = 0;
         // the column one step ahead: its symbol (and byte table) is fetched while the current column is computed
@@ -162,7 +193,10 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
             if (top) {
                 if ((s & 31) == 0) {
                     top_cur = top_nxt;
-                    if (s + 33 + lane <= c.ncols) top_nxt = top[s + 33 + lane];
+                    if (s + 33 <= c.ncols) {
+                        wait_top(s + 64);
+                        if (s + 33 + lane <= c.ncols) top_nxt = __ldcg(top + s + 33 + lane);
+                    }
                 }
                 const int t0 = __shfl_sync(0xffffffffu, top_cur, s & 31);  // top[s + 1]: lane 0 is at column s + 1
                 if (lane == 0) up_in = t0;
@@ -198,7 +232,13 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
                     H[r] = h;
                 }
             }
-            if (bot && lane == 31) bot[j] = H[R - 1];
+            if (bot && lane == 31) {
+                bot[j] = H[R - 1];
+                if ((j & 31) == 0 || j == c.ncols) {  // publish: the row is complete up to column j
+                    __threadfence();  // the consumer reads the row from L2 (ld.cg): the stores must have got there
+                    *prog_out = (long long)b * stride + j;
+                }
+            }
             pmax = max(pmax, H[R - 1] - g * j);
 
             // candidate column?
@@ -251,7 +291,6 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, int g) {
         // whole prefix through a free s2 begin), including the border cell
         if (c.kind == PASS_DUMP && b == NB - 1 && lane == 31)
             c.B[c.n1 + 1] = max(pmax - g * (NB * RB), border_col0(c, c.n1, g));
-        __syncwarp();  // boundary row written by lane 31 is read by lane 0 in the next pass
     }
 }
 
@@ -267,14 +306,12 @@ __device__ inline bool rows_have_classes(const unsigned char *s1, int n1, const 
 // fl + motif*n_hi vs db combines at every candidate column.  `flags` = STRK_*_FREE end flags.
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__device__ void process_read_family(const FamDesc &f, const unsigned char *arena, const GenSmem &sc, int g,
+__device__ void process_read_family(const FamDesc &f, const unsigned char *arena, const GenSmem &sc, GenSync &sy, int g,
                                     int flags, int *table, int *scratch, int scratch_rowlen, int scratch_b_len) {
-    const int lane = threadIdx.x & 31;
     const int n1 = f.n_fl + f.n_tr + f.n_fr;
     const int W = f.n_hi - f.n_lo + 1;
     int *out = table + f.out_off;
-    for (int k = lane; k < W; k += 32) out[k] = STRK_NEG_INF;
-    __syncwarp();
+    for (int k = threadIdx.x; k < W; k += blockDim.x) out[k] = STRK_NEG_INF;  // (dp_pass opens with a barrier)
 
     const bool lut_ok = rows_have_classes(arena + f.db_off, n1, sc);
     PassCfg c;
@@ -283,8 +320,8 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
     c.motif = arena + f.motif_off;
     c.m = f.m;
     c.B = scratch;
-    c.row0 = scratch + scratch_b_len;
-    c.row1 = c.row0 + scratch_rowlen;
+    c.rows = scratch + scratch_b_len;
+    c.rowlen = scratch_rowlen;
     c.out = out;
     c.out64 = nullptr;
     c.n_lo = f.n_lo;
@@ -303,10 +340,9 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
     c.kind = PASS_DUMP;
     c.lastrow_term = 0;
     if (lut_ok)
-        dp_pass<R, true>(c, sc, g);
+        dp_pass<R, true>(c, sc, sy, g);
     else
-        dp_pass<R, false>(c, sc, g);
-    __syncwarp();
+        dp_pass<R, false>(c, sc, sy, g);
 
     // forward sweep
     c.pre = arena + f.db_off;
@@ -320,10 +356,9 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
     c.kind = PASS_COMBINE;
     c.lastrow_term = (flags & 8) != 0;
     if (lut_ok)
-        dp_pass<R, true>(c, sc, g);
+        dp_pass<R, true>(c, sc, sy, g);
     else
-        dp_pass<R, false>(c, sc, g);
-    __syncwarp();
+        dp_pass<R, false>(c, sc, sy, g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -332,14 +367,12 @@ __device__ void process_read_family(const FamDesc &f, const unsigned char *arena
 //   rev: columns reverse(fr) + reverse(motif)*n   rows reverse(db)   -> out64[2*k + 1]
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__device__ void process_ref_family(const FamDesc &f, const unsigned char *arena, const GenSmem &sc, int g,
+__device__ void process_ref_family(const FamDesc &f, const unsigned char *arena, const GenSmem &sc, GenSync &sy, int g,
                                    long long *table, int *scratch, int scratch_rowlen, int scratch_b_len) {
-    const int lane = threadIdx.x & 31;
     const int n1 = f.n_fl + f.n_tr + f.n_fr;
     const int W = f.n_hi - f.n_lo + 1;
     long long *out = table + 2 * f.out_off;
-    for (int k = lane; k < 2 * W; k += 32) out[k] = (long long)0x8000000000000000ull;
-    __syncwarp();
+    for (int k = threadIdx.x; k < 2 * W; k += blockDim.x) out[k] = (long long)0x8000000000000000ull;
 
     const bool lut_ok = rows_have_classes(arena + f.db_off, n1, sc);
     PassCfg c;
@@ -348,8 +381,8 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     c.motif = arena + f.motif_off;
     c.m = f.m;
     c.B = nullptr;
-    c.row0 = scratch + scratch_b_len;
-    c.row1 = c.row0 + scratch_rowlen;
+    c.rows = scratch + scratch_b_len;
+    c.rowlen = scratch_rowlen;
     c.out = nullptr;
     c.n_lo = f.n_lo;
     c.n_hi = f.n_hi;
@@ -367,10 +400,9 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     c.ncols = f.n_fl + f.m * f.n_hi;
     c.out64 = out;
     if (lut_ok)
-        dp_pass<R, true>(c, sc, g);
+        dp_pass<R, true>(c, sc, sy, g);
     else
-        dp_pass<R, false>(c, sc, g);
-    __syncwarp();
+        dp_pass<R, false>(c, sc, sy, g);
 
     c.pre = arena + f.db_off + f.n_fl + f.n_tr;
     c.n_pre = f.n_fr;
@@ -380,15 +412,14 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     c.ncols = f.n_fr + f.m * f.n_hi;
     c.out64 = out + W;
     if (lut_ok)
-        dp_pass<R, true>(c, sc, g);
+        dp_pass<R, true>(c, sc, sy, g);
     else
-        dp_pass<R, false>(c, sc, g);
-    __syncwarp();
+        dp_pass<R, false>(c, sc, sy, g);
 }
 
-// Persistent kernel: warps pull families from a cost-sorted queue.
+// Persistent kernel: CTAs (GEN_WARPS warps on one family) pull families from a cost-sorted queue.
 template <bool REF>
-__global__ void __launch_bounds__(32, 16) dp_general_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ order,
+__global__ void __launch_bounds__(GEN_WARPS * 32, 16 / GEN_WARPS) dp_general_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ order,
                                                          int n_fams, const unsigned char *__restrict__ arena,
                                                          const ScoreConsts *__restrict__ consts, void *table,
                                                          int *scratch, int scratch_rowlen, int scratch_b_len,
@@ -396,6 +427,7 @@ __global__ void __launch_bounds__(32, 16) dp_general_kernel(const FamDesc *__res
                                                          const unsigned int *__restrict__ n_fams_dev) {
     if (n_fams_dev) n_fams = (int)*n_fams_dev;  // list length produced on the device (packed-kernel fallbacks)
     __shared__ GenSmem sc;
+    __shared__ GenSync sy;
     const int g = consts->gap;
     for (int k = threadIdx.x; k < 256; k += blockDim.x) sc.lut[k] = consts->lut[k];
     for (int k = threadIdx.x; k < STRK_SMAT_ROWS * STRK_NSYM_; k += blockDim.x) sc.smat2[k] = (short)(consts->smat[k] + 2 * g);
@@ -405,14 +437,13 @@ __global__ void __launch_bounds__(32, 16) dp_general_kernel(const FamDesc *__res
     if (threadIdx.x == 0) sc.one = consts->one_v[0];
     __syncthreads();
     const int flags = consts->end_flags;
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int *my_scratch = scratch + (size_t)warp_global * (size_t)(scratch_b_len + 2 * scratch_rowlen);
+    int *my_scratch = scratch + (size_t)blockIdx.x * ((size_t)scratch_b_len + (size_t)GEN_RING * scratch_rowlen);
 
     for (;;) {
-        unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(queue, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
+        __syncthreads();  // every warp is done with the previous family (and has read sy.q)
+        if (threadIdx.x == 0) sy.q = atomicAdd(queue, 1u);
+        __syncthreads();
+        const unsigned int q = sy.q;
         if (q >= (unsigned)n_fams) break;
         const FamDesc f = fams[order ? order[q] : (int)q];
         const int n1 = f.n_fl + f.n_tr + f.n_fr;
@@ -420,10 +451,10 @@ __global__ void __launch_bounds__(32, 16) dp_general_kernel(const FamDesc *__res
 #define STRK_CASE(RR)                                                                                          \
     case RR:                                                                                                   \
         if (REF)                                                                                               \
-            process_ref_family<RR>(f, arena, sc, g, (long long *)table, my_scratch, scratch_rowlen,            \
+            process_ref_family<RR>(f, arena, sc, sy, g, (long long *)table, my_scratch, scratch_rowlen,        \
                                    scratch_b_len);                                                             \
         else                                                                                                   \
-            process_read_family<RR>(f, arena, sc, g, flags, (int *)table, my_scratch, scratch_rowlen,          \
+            process_read_family<RR>(f, arena, sc, sy, g, flags, (int *)table, my_scratch, scratch_rowlen,      \
                                     scratch_b_len);                                                            \
         break;
         switch (R) {
