@@ -65,13 +65,27 @@ class ReadBatch:
                          self.motif_len[lo:hi].copy())
 
 
-def pack_loci(loci: Iterable[LocusReads]) -> ReadBatch:
-    """Pack per-locus string tuples into one arena.  The per-read Python work is kept to list building done by
-    C-level iterators (zip / chain / map): one str.join + one encode for all sequences, lengths through
-    np.fromiter(map(len, ...)).  (strkit_b200.synth builds fully vectorised synthetic batches.)"""
+try:  # CPython helper built by __graft_entry__.build() (csrc/fastpack.c): two passes over the objects, no temporaries
+    from . import _fastpack
+except ImportError:  # not built: the pure-Python body below does the same, ~6x slower
+    _fastpack = None
+
+
+def pack_loci(loci: Iterable[LocusReads], use_helper: bool = True) -> ReadBatch:
+    """Pack per-locus string tuples into one arena.  With the C helper: one sizing pass and one copying pass over
+    the Python objects.  Without it the per-read Python work is kept to list building done by C-level iterators
+    (zip / chain / map): one str.join + one encode for all sequences, lengths through np.fromiter(map(len, ...)).
+    (strkit_b200.synth builds fully vectorised synthetic batches.)"""
     from itertools import chain
 
     loci = list(loci)
+    if _fastpack is not None and use_helper:
+        arena, seq_off, lens, est, read_begin, motif_off, motif_len = _fastpack.pack(loci)
+        return ReadBatch(arena=np.frombuffer(arena, dtype=np.uint8), seq_off=np.frombuffer(seq_off, dtype=np.uint64),
+                         lens=np.frombuffer(lens, dtype=np.int32).reshape(-1, 3),
+                         est_cn=np.frombuffer(est, dtype=np.int32), read_begin=np.frombuffer(read_begin, dtype=np.int64),
+                         motif_off=np.frombuffer(motif_off, dtype=np.uint64),
+                         motif_len=np.frombuffer(motif_len, dtype=np.int32))
     n_per = []
     for lr in loci:
         n = len(lr.tr_seqs)

@@ -80,6 +80,42 @@ def test_pack_loci_layout():
     assert s.n_reads == 1 and s.read_begin.tolist() == [0, 1] and s.lens.tolist() == [[0, 2, 2]]
 
 
+def test_pack_loci_c_helper_equals_python_body():
+    """csrc/fastpack.c (built by __graft_entry__.build()) and the pure-Python body of pack_loci produce the same
+    arrays: ragged loci, empty strings, a locus without reads, tuples instead of lists, numpy estimates."""
+    import importlib
+
+    import __graft_entry__
+    from strkit_b200 import LocusReads, batcher
+    from tests.helpers import random_families
+
+    if batcher._fastpack is None:  # first run in a fresh tree
+        __graft_entry__.build()
+        importlib.reload(batcher)
+    assert batcher._fastpack is not None, "build() should have compiled strkit_b200/_fastpack.so"
+    pack_loci = batcher.pack_loci
+    rng = np.random.default_rng(9)
+    fams = random_families(rng, 300)
+    loci, at = [], 0
+    while at < len(fams):
+        n = int(rng.integers(0, 6))
+        grp = fams[at:at + n]
+        at += n
+        motif = grp[0][0] if grp else "ACG"
+        loci.append(LocusReads(motif, np.array([len(t) // len(motif) for _, t, _, _ in grp], dtype=np.int64),
+                               tuple(t for _, t, _, _ in grp), [fl for _, _, fl, _ in grp], [fr for _, _, _, fr in grp]))
+    for subset in (loci, loci[:1], []):
+        a, b = pack_loci(subset, use_helper=True), pack_loci(subset, use_helper=False)
+        for f in ("arena", "seq_off", "lens", "est_cn", "read_begin", "motif_off", "motif_len"):
+            x, y = getattr(a, f), getattr(b, f)
+            assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y), f
+        a.validate()
+    with pytest.raises(ValueError):
+        pack_loci([LocusReads("AC", [1], ["AC\u00e9"], ["A"], ["C"])])
+    with pytest.raises(ValueError):
+        pack_loci([LocusReads("AC", [1, 2], ["AC"], ["A"], ["C"])])
+
+
 def test_synth_generator_is_deterministic_and_sane(oracle):
     from strkit_b200 import synth
 
