@@ -244,6 +244,50 @@ def test_long_expansions_multi_pass(sb, oracle):
     assert np.array_equal(got, want), (got[:8], want[:8])
 
 
+@pytest.mark.parametrize("flags", [0, 6, 9, 15])
+def test_general_kernel_many_strips(sb, oracle, flags):
+    """Reads of 6 to 13 strips of 512 rows: the strips run as a pipeline over the 4 warps of a CTA and the ring of
+    boundary rows (5 slots) is reused -- DUMP / COMBINE sweeps here, ARGMAX in the reference-boundary test below."""
+    rng = np.random.default_rng(300 + flags)
+    fams, n_lo, n_hi = [], [], []
+    for k, motif in ((520, "CAGGT"), (1400, "AAG"), (1290, "GGCCT"), (2200, "CTG"), (6100, "A")):
+        tr = mutate(rng, motif * k, 0.01, 0.005, 0.005)
+        if k == 1400:
+            tr = "".join("X" if rng.random() < 0.01 else ("R" if rng.random() < 0.002 else ch) for ch in tr)  # look-up path
+        fl = "".join(rng.choice(list("ACGT"), size=70))
+        fr = "".join(rng.choice(list("ACGT"), size=int(rng.integers(1, 71))))
+        fams.append((motif, tr, fl, fr))
+        e = round(len(tr) / len(motif))
+        n_lo.append(e - 1)
+        n_hi.append(e + 1)
+    eng = sb.Engine(end_flags=flags)
+    got, _ = eng.score_tables(families_to_batch(fams), np.array(n_lo), np.array(n_hi), kernel=sb.KERNEL_GENERAL)
+    want = oracle_tables(oracle, fams, n_lo, n_hi, flags)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    eng.close()
+
+
+def test_ref_boundary_tables_many_strips(sb, oracle):
+    """score_ref_boundaries on reference windows of 7 and 10 strips (ARGMAX sweeps of the general kernel)."""
+    rng = np.random.default_rng(77)
+    fams, ns = [], []
+    for k, motif in ((1100, "CAG"), (980, "GGCCT")):
+        tr = mutate(rng, motif * k, 0.004, 0.002, 0.002)
+        fams.append((motif, tr, "".join(rng.choice(list("ACGT"), size=70)), "".join(rng.choice(list("ACGT"), size=70))))
+        ns.append(round(len(tr) / len(motif)))
+    ns = np.array(ns)
+    eng = sb.Engine()
+    tab, off = eng.ref_boundary_tables(families_to_batch(fams), ns - 1, ns + 1)
+    for i, (motif, tr, fl, fr) in enumerate(fams):
+        ref_size = len(tr)
+        for n in range(int(ns[i]) - 1, int(ns[i]) + 2):
+            (ofs, ora), (ors, ola) = oracle.score_ref_boundaries(tr, fl, fr, motif, n, ref_size)
+            fs, fe, rs, re = (int(v) for v in tab[int(off[i]) + n - int(ns[i]) + 1])
+            assert (fs, fe + 1 - len(fl) - ref_size) == (ofs, ora)
+            assert (rs, re + 1 - len(fr) - ref_size) == (ors, ola)
+    eng.close()
+
+
 def test_ref_boundary_tables_golden(sb, oracle, golden):
     eng = sb.Engine()
     fams = [(c["motif"], c["tr_seq"], c["flank_left_seq"], c["flank_right_seq"]) for c in golden["boundaries"]]
