@@ -530,6 +530,76 @@ static int launch_packed(strk_ctx *ctx, int R, const FamDesc *fams, const int *l
     }
 }
 
+// One launch per rows-per-lane class k >= 1 of a pass (list[k], cnt[k]; tables sized by flank[k], mmax[k], w_max[k]);
+// a class whose tables do not fit shared memory goes to the general kernel.  Large passes: back to back on the
+// run's stream (spreading the classes over several streams was measured slower there, -2.8 %: concurrent grids with
+// different footprints fragment the SMs).  Small passes, where a class is less than a wave of CTAs and each launch
+// lasts one read's sweep whatever its grid: every class on its own side stream with its own slice of the capture
+// scratch, so the launches overlap (blocks of a few hundred loci, per-locus calls, second passes, the reference path).
+static int launch_packed_classes(strk_ctx *ctx, const int *const *list, const long long *cnt, const int *flank,
+                                 const int *mmax, const int *w_max, long long n_slots, const FamDesc *fams,
+                                 const unsigned char *arena, void *table, int b_len, int rowlen, cudaStream_t st,
+                                 int ref_mode, long long *n_packed) {
+    static const long long fan_max = [] {
+        const char *e = getenv("STRK_PK_FANOUT_MAX");  // reads per pass up to which the classes overlap
+        return e ? atoll(e) : 131072LL;
+    }();
+    int rc = STRK_OK;
+    long long fan_off[STRK_PK_NBIN];
+    bool fan_out = false;
+    if (n_slots <= fan_max) {
+        size_t total = 0;
+        int n_classes = 0;
+        for (int k = STRK_PK_RMAX; k >= 1; --k) {
+            fan_off[k] = -1;
+            if (!cnt[k]) continue;
+            const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], w_max[k]);
+            if (pk_smem_for_class(k, dims) > 200 * 1024) continue;
+            size_t need = 0;
+            rc = launch_packed(ctx, k, fams, list[k], (int)cnt[k], arena, (int *)table, dims, st, ref_mode, &need);
+            if (rc) return rc;
+            fan_off[k] = (long long)total;
+            total += need;
+            ++n_classes;
+        }
+        if (n_classes >= 2) {
+            if (ctx->pk_scratch.reserve(total) != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", total * sizeof(uint4));
+            }
+            if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(ctx->fork_ev, st));
+            fan_out = true;
+        }
+    }
+    for (int k = STRK_PK_RMAX; k >= 1; --k) {
+        if (!cnt[k]) continue;
+        const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], w_max[k]);
+        if (fan_out && fan_off[k] >= 0) {
+            if (!ctx->side[k]) CU(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+            if (!ctx->side_ev[k]) CU(cudaEventCreateWithFlags(&ctx->side_ev[k], cudaEventDisableTiming));
+            CU(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev, 0));
+            rc = launch_packed(ctx, k, fams, list[k], (int)cnt[k], arena, (int *)table, dims, ctx->side[k], ref_mode, nullptr,
+                               fan_off[k]);
+            if (rc) return rc;
+            CU(cudaEventRecord(ctx->side_ev[k], ctx->side[k]));
+            CU(cudaStreamWaitEvent(st, ctx->side_ev[k], 0));
+            *n_packed += cnt[k];
+            continue;
+        }
+        if (pk_smem_for_class(k, dims) > 200 * 1024) {
+            // shared memory would not fit: hand the whole segment to the general kernel
+            rc = launch_general(ctx, ref_mode != 0, fams, list[k], cnt[k], arena, table, b_len, rowlen, st);
+            if (rc) return rc;
+            continue;
+        }
+        rc = launch_packed(ctx, k, fams, list[k], (int)cnt[k], arena, (int *)table, dims, st, ref_mode);
+        if (rc) return rc;
+        *n_packed += cnt[k];
+    }
+    return STRK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // batches
 // ------------------------------------------------------------------------------------------------
@@ -913,70 +983,11 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
                 for (int k = 0; k < STRK_PK_NBIN; ++k) seg_list[k] = ctx->list_d.p + at[k], seg_cnt[k] = (long long)by_class[k].size();
             }
             CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
-            // One launch per rows-per-lane class.  Large passes: back to back on the run's stream (spreading the
-            // classes over several streams was measured slower there, -2.8 %: concurrent grids with different
-            // footprints fragment the SMs).  Small passes, where a class is less than a wave of CTAs and each launch
-            // lasts one read's sweep whatever its grid: every class on its own side stream with its own slice of
-            // the capture scratch, so the launches overlap (blocks of a few hundred loci, per-locus calls).
-            static const long long fan_max = [] {
-                const char *e = getenv("STRK_PK_FANOUT_MAX");  // reads per pass up to which the classes overlap
-                return e ? atoll(e) : 131072LL;
-            }();
-            long long fan_off[STRK_PK_NBIN];
-            bool fan_out = false;
-            if (n_slots <= fan_max) {
-                size_t total = 0;
-                int n_classes = 0;
-                for (int k = STRK_PK_RMAX; k >= 1; --k) {
-                    fan_off[k] = -1;
-                    if (!seg_cnt[k]) continue;
-                    const PackedDims dims = pk_dims_for_class(k, seg_flank[k], seg_mmax[k], (W + 3) / 4 * 4);
-                    if (pk_smem_for_class(k, dims) > 200 * 1024) continue;
-                    size_t need = 0;
-                    rc = launch_packed(ctx, k, ctx->fams.p, seg_list[k], (int)seg_cnt[k], b->d_arena, ctx->table.p, dims, st, 0,
-                                       &need);
-                    if (rc) return rc;
-                    fan_off[k] = (long long)total;
-                    total += need;
-                    ++n_classes;
-                }
-                if (n_classes >= 2) {
-                    if (ctx->pk_scratch.reserve(total) != cudaSuccess) {
-                        cudaGetLastError();
-                        return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of capture scratch", total * sizeof(uint4));
-                    }
-                    if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-                    CU(cudaEventRecord(ctx->fork_ev, st));
-                    fan_out = true;
-                }
-            }
-            for (int k = STRK_PK_RMAX; k >= 1; --k) {
-                if (!seg_cnt[k]) continue;
-                const int R = k;
-                const PackedDims dims = pk_dims_for_class(R, seg_flank[k], seg_mmax[k], (W + 3) / 4 * 4);
-                if (fan_out && fan_off[k] >= 0) {
-                    if (!ctx->side[k]) CU(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-                    if (!ctx->side_ev[k]) CU(cudaEventCreateWithFlags(&ctx->side_ev[k], cudaEventDisableTiming));
-                    CU(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev, 0));
-                    rc = launch_packed(ctx, R, ctx->fams.p, seg_list[k], (int)seg_cnt[k], b->d_arena, ctx->table.p, dims,
-                                       ctx->side[k], 0, nullptr, fan_off[k]);
-                    if (rc) return rc;
-                    CU(cudaEventRecord(ctx->side_ev[k], ctx->side[k]));
-                    CU(cudaStreamWaitEvent(st, ctx->side_ev[k], 0));
-                    n_packed += seg_cnt[k];
-                    continue;
-                }
-                if (pk_smem_for_class(R, dims) > 200 * 1024) {
-                    // shared memory would not fit: hand the whole segment to the general kernel
-                    rc = launch_general(ctx, false, ctx->fams.p, seg_list[k], seg_cnt[k], b->d_arena, ctx->table.p, b_len,
-                                        rowlen, st);
-                    if (rc) return rc;
-                    continue;
-                }
-                rc = launch_packed(ctx, R, ctx->fams.p, seg_list[k], (int)seg_cnt[k], b->d_arena, ctx->table.p, dims, st);
-                if (rc) return rc;
-                n_packed += seg_cnt[k];
-            }
+            int seg_w[STRK_PK_NBIN];
+            for (int k = 0; k < STRK_PK_NBIN; ++k) seg_w[k] = (W + 3) / 4 * 4;
+            rc = launch_packed_classes(ctx, seg_list, seg_cnt, seg_flank, seg_mmax, seg_w, n_slots, ctx->fams.p, b->d_arena,
+                                       ctx->table.p, b_len, rowlen, st, 0, &n_packed);
+            if (rc) return rc;
             rc = launch_general(ctx, false, ctx->fams.p, seg_list[0], seg_cnt[0], b->d_arena, ctx->table.p, b_len, rowlen, st);
             if (rc) return rc;
             if (n_packed) {
@@ -1430,21 +1441,17 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
                 CU(cudaMemcpyAsync(d_lists, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
                 CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
                 long long n_packed = 0;
-                for (int k = STRK_PK_RMAX; k >= 1; --k) {
-                    if (lists[k].empty()) continue;
-                    // w_max: forward + reverse columns of every size of the window
-                    const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], 2 * stride_w - 1);
-                    if (pk_smem_for_class(k, dims) > 200 * 1024) {
-                        rc = launch_general(ctx, true, ctx->fams.p, d_lists + at[k], (long long)lists[k].size(), d_arena,
-                                            ctx->table64.p, b_len, rowlen, st);
-                        if (rc) return rc;
-                        continue;
-                    }
-                    rc = launch_packed(ctx, k, ctx->fams.p, d_lists + at[k], (int)lists[k].size(), d_arena,
-                                       (int *)ctx->table64.p, dims, st, 1);
-                    if (rc) return rc;
-                    n_packed += (long long)lists[k].size();
+                const int *seg_list[STRK_PK_NBIN];
+                long long seg_cnt[STRK_PK_NBIN];
+                int seg_w[STRK_PK_NBIN];
+                for (int k = 0; k < STRK_PK_NBIN; ++k) {
+                    seg_list[k] = d_lists + at[k];
+                    seg_cnt[k] = (long long)lists[k].size();
+                    seg_w[k] = 2 * stride_w - 1;  // forward + reverse columns of every size of the window
                 }
+                rc = launch_packed_classes(ctx, seg_list, seg_cnt, flank, mmax, seg_w, n_loci, ctx->fams.p, d_arena,
+                                           ctx->table64.p, b_len, rowlen, st, 1, &n_packed);
+                if (rc) return rc;
                 rc = launch_general(ctx, true, ctx->fams.p, d_lists + at[0], (long long)lists[0].size(), d_arena,
                                     ctx->table64.p, b_len, rowlen, st);
                 if (rc) return rc;
