@@ -79,6 +79,9 @@ int strk_device_count(void);
 int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM], int gap_open, int gap_extend, int end_flags,
               int tie_flags, strk_ctx **ctx);
 int strk_destroy(strk_ctx *ctx);
+/* Wait for everything queued on the context's streams (SURVEY 8b minimum set).  Every entry point of this header
+ * returns with its results in the caller's buffers, so this only matters after strk_batch_run on a caller stream. */
+int strk_sync(strk_ctx *ctx);
 
 /* Pin / unpin a caller-owned host buffer so that copies are asynchronous DMA. */
 int strk_host_register(void *ptr, uint64_t bytes);

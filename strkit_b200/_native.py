@@ -38,6 +38,7 @@ def _load() -> C.CDLL:
         "strk_device_count": (C.c_int, []),
         "strk_init": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
         "strk_destroy": (C.c_int, [_vp]),
+        "strk_sync": (C.c_int, [_vp]),
         "strk_host_register": (C.c_int, [_vp, _u64]),
         "strk_host_unregister": (C.c_int, [_vp]),
         "strk_batch_upload": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, C.POINTER(_vp)]),
@@ -68,7 +69,7 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
-EXPORTED = ("strk_last_error", "strk_version", "strk_device_count", "strk_init", "strk_destroy", "strk_host_register",
+EXPORTED = ("strk_last_error", "strk_version", "strk_device_count", "strk_init", "strk_destroy", "strk_sync", "strk_host_register",
             "strk_host_unregister", "strk_batch_upload", "strk_batch_create", "strk_batch_fill", "strk_batch_run", "strk_batch_download", "strk_batch_free",
             "strk_count_reads", "strk_score_tables", "strk_ref_boundary_tables", "strk_ref_counts", "strk_call_alleles", "strk_gmm_fit_counts",
             "strk_alleles_aggregate", "strk_get_stats", "strk_measure_int_peak")

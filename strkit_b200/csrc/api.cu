@@ -279,6 +279,15 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
 
 extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b);
 
+extern "C" int strk_sync(strk_ctx *ctx) {
+    if (!ctx) return set_err(STRK_ERR_ARG, "strk_sync: null context");
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < STRK_PK_NBIN; ++k)
+        if (ctx->side[k]) CU(cudaStreamSynchronize(ctx->side[k]));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return STRK_OK;
+}
+
 extern "C" int strk_destroy(strk_ctx *ctx) {
     if (!ctx) return STRK_OK;
     cudaSetDevice(ctx->device);

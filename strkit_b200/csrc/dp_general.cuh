@@ -54,7 +54,9 @@ struct PassCfg {
 // in the ring slot b % GEN_RING.  A long read (config 4: 12 strips of 6 200 columns) is bound by the latency of its
 // own dependency chain, so four strips in flight cut its time almost four-fold.  progress[slot] = b * stride + last
 // column written: values only grow over the strips that reuse a slot, so a stale value never satisfies a waiter.
+#ifndef GEN_WARPS
 #define GEN_WARPS 4
+#endif
 #define GEN_RING (GEN_WARPS + 1)
 struct GenSync {
     volatile long long progress[GEN_RING];
