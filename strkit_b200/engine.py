@@ -63,6 +63,12 @@ class Engine:
         self._stream_batch = None                # reusable strk_batch of this context
         self._run_lock = threading.Lock()
 
+    def sync(self) -> None:
+        """Wait for everything queued on the context's streams (strk_sync)."""
+        check(lib.strk_sync(self._ctx))
+        if getattr(self, "_twin", None):
+            self._twin.sync()
+
     def close(self) -> None:
         if getattr(self, "_twin", None):
             self._twin.close()
