@@ -484,6 +484,7 @@ done:
  * :1148-1155 (call), :1161 (offset update).  Float64 arithmetic as in CPython.
  * ------------------------------------------------------------------------------------------- */
 #define LOCI_BLOCK 16
+#define LOCUS_MEMO 512 /* reads of a locus the per-locus call memo covers (the reference keeps at most 250 reads) */
 
 typedef struct {
     const char *arena;
@@ -500,6 +501,7 @@ typedef struct {
     int32_t *out;
     double cells;
     int rc;
+    double read_cells[LOCUS_MEMO]; /* cells scored by each memoised call of the current locus */
 } loci_job;
 
 static void *loci_worker(void *arg) {
@@ -522,12 +524,33 @@ static void *loci_worker(void *arg) {
             const char *db = jb->arena + jb->seq_off[r];
             int nfl = jb->lens[3 * r], ntr = jb->lens[3 * r + 1], nfr = jb->lens[3 * r + 2];
             int32_t r4[4] = {0, 0, 0, 0};
-            int rc = get_repeat_count_cells(read_sc, db, nfl + ntr + nfr, db, nfl, db + nfl + ntr, nfr, motif, m,
-                                            jb->max_iters, jb->range, jb->step, jb->gap, jb->matrix, jb->flags,
-                                            jb->tie_flags, r4, &jb->cells);
-            if (rc) {
-                jb->rc = rc;
-                return NULL;
+            /* The reference wraps get_repeat_count in lru_cache(maxsize=512) (repeats.py:47): a call whose start count
+             * and sequences equal an earlier call's is answered from the cache.  Hits across loci need equal flanks,
+             * so the memo here is per locus.  `cells` keeps counting what the call would have scored (the GPU side
+             * reports reference-equivalent cells per read the same way). */
+            int64_t hit = -1;
+            for (int64_t p = jb->read_begin[l]; p < r && p - jb->read_begin[l] < LOCUS_MEMO && hit < 0; ++p) {
+                if (jb->out[4 * p + 3] == read_sc && jb->lens[3 * p] == nfl && jb->lens[3 * p + 1] == ntr &&
+                    jb->lens[3 * p + 2] == nfr &&
+                    memcmp(jb->arena + jb->seq_off[p], db, (size_t)(nfl + ntr + nfr)) == 0)
+                    hit = p;
+            }
+            if (hit >= 0) {
+                r4[0] = jb->out[4 * hit + 0];
+                r4[1] = jb->out[4 * hit + 1];
+                r4[2] = jb->out[4 * hit + 2];
+                r4[3] = r4[0] - read_sc;
+                jb->cells += jb->read_cells[hit - jb->read_begin[l]];
+            } else {
+                const double before = jb->cells;
+                int rc = get_repeat_count_cells(read_sc, db, nfl + ntr + nfr, db, nfl, db + nfl + ntr, nfr, motif, m,
+                                                jb->max_iters, jb->range, jb->step, jb->gap, jb->matrix, jb->flags,
+                                                jb->tie_flags, r4, &jb->cells);
+                if (rc) {
+                    jb->rc = rc;
+                    return NULL;
+                }
+                if (r - jb->read_begin[l] < LOCUS_MEMO) jb->read_cells[r - jb->read_begin[l]] = jb->cells - before;
             }
             jb->out[4 * r + 0] = r4[0];
             jb->out[4 * r + 1] = r4[1];
@@ -560,7 +583,7 @@ int strk_oracle_count_loci(const char *arena, const uint64_t *seq_off, const int
     int64_t next_block = 0;
     for (int t = 0; t < n_threads; ++t) {
         jobs[t] = (loci_job){arena, seq_off, lens, est_cn, read_begin, motif_off, motif_len, n_loci, &next_block,
-                             max_iters, local_search_range, step_size, gap, flags, tie_flags, matrix, out, 0.0, 0};
+                             max_iters, local_search_range, step_size, gap, flags, tie_flags, matrix, out, 0.0, 0, {0.0}};
     }
     if (n_threads == 1) {
         loci_worker(&jobs[0]);
