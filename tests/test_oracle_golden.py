@@ -127,3 +127,33 @@ def test_read_loop_carries_offset(oracle):
     # read 0 starts at 22; the -2/20 fraction moves later starts: round(-0.1*22) = -2
     assert out[:, 3].tolist() == [22, 20, 21, 20]
     assert cells > 0
+
+
+def test_locus_memo_equals_per_call_search(oracle):
+    """The batch loop answers identical calls of a locus from a memo (the reference's lru_cache, repeats.py:47);
+    every row must equal the per-call search replayed here with the carried offset of call_locus.py:1129-1161."""
+    from strkit_b200 import synth
+
+    b = synth.generate(synth.CONFIGS[2], 60, seed=17).to_host()   # HiFi-like: a third of the reads are duplicates
+    out, _ = oracle.count_loci(b.arena, b.seq_off, b.lens, b.est_cn, b.read_begin, b.motif_off, b.motif_len, n_threads=4)
+    arena = b.arena.tobytes()
+    dup = 0
+    for l in range(b.n_loci):
+        motif = arena[int(b.motif_off[l]):int(b.motif_off[l]) + int(b.motif_len[l])].decode()
+        frac, seen = 0.0, set()
+        for r in range(int(b.read_begin[l]), int(b.read_begin[l + 1])):
+            o, (nfl, ntr, nfr) = int(b.seq_off[r]), (int(v) for v in b.lens[r])
+            fl, tr, fr = (arena[o:o + nfl].decode(), arena[o + nfl:o + nfl + ntr].decode(),
+                          arena[o + nfl + ntr:o + nfl + ntr + nfr].decode())
+            start = int(b.est_cn[r])
+            off = round(frac * start)
+            if off < -start:
+                frac = 0.0
+            else:
+                start += off
+            dup += (start, fl, tr, fr) in seen
+            seen.add((start, fl, tr, fr))
+            (n, score), n_explored, delta = oracle.get_repeat_count(start, tr, fl, fr, motif, 50, 3, 1)
+            assert out[r].tolist() == [n, score, n_explored, start], (l, r)
+            frac += delta / max(n, 1)
+    assert dup > 0.2 * b.n_reads  # the memo was exercised
