@@ -163,3 +163,30 @@ def test_install_rebinds_strkit_names(monkeypatch):
     assert len(patched) == 6 and loc.call_alleles is strkit_b200.call_alleles and al.call_alleles is strkit_b200.call_alleles
     strkit_b200.uninstall()
     assert loc.call_alleles() == "reference" and al.call_alleles() == "reference"
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line on stdout with the
+    contract's keys, exactly K timed steps; ranks other than 0 print nothing."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--cpu-sample-loci", "48"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
+    for key in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "vs_baseline", "dtype", "data"):
+        assert key in d, key
+    assert "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"),
+                         timeout=600)
+    assert out.returncode == 0 and out.stdout.strip() == ""
