@@ -377,7 +377,10 @@ def main():
     if full_affinity is not None:
         os.sched_setaffinity(0, full_affinity)
     if rank == 0 and not args.no_cpu_baseline:
-        cpu, want, sub = cpu_baseline(host_batches[0], args.cpu_sample_loci)
+        # the timed CPU baseline belongs to the N = 1 line; multi-GPU runs keep a small bit-exactness sample only
+        cpu, want, sub = cpu_baseline(host_batches[0], args.cpu_sample_loci if world == 1 else min(256, args.cpu_sample_loci))
+        if world > 1:
+            cpu = None
         got = eng.download(dev_batches[0])[:sub.n_reads] if args.warmup + args.steps > 0 else None
         if args.pool and (args.steps + args.warmup) > 0:
             # batch 0 was last run in the timed loop or warm-up; its device results are still resident
