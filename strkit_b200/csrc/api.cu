@@ -956,8 +956,9 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         const bool use_packed = kernel != STRK_KERNEL_GENERAL && ctx->h_consts.packed_ok && W <= PK_WINDOW_MAX;
         long long n_packed = 0;
         if (!use_packed) {
-            rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots, b->d_arena, ctx->table.p,
-                                b_len, rowlen, st);
+            // (first pass: the work order lists the representatives only when identical reads share tables)
+            rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots - (pass == 0 ? b->n_dup : 0),
+                                b->d_arena, ctx->table.p, b_len, rowlen, st);
             if (rc) return rc;
         } else {
             // Packed kernel per rows-per-lane class; what it cannot take goes to the general kernel.
