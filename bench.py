@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--loci-per-step", type=int, default=32768)
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through (> L2)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "general"])
-    ap.add_argument("--cpu-sample-loci", type=int, default=768)
+    ap.add_argument("--cpu-sample-loci", type=int, default=4096,
+                    help="loci of batch 0 the CPU port runs (6-7 s on 16 cores, ~25 s on 8 slow ones)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = the same number of blocks as --steps")
@@ -152,15 +153,21 @@ def run_reference(args):
 
     from strkit_b200 import synth
 
-    n_sample = args.cpu_sample_loci
     t_all = time.perf_counter()
-    batch = synth.generate(synth.CONFIGS[2], n_sample, seed=20261018 + 2000, device="cpu").to_host()
     from tests import oracle_lib
 
     orc = oracle_lib.load()
     cores = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 4))
-    warm = min(args.warmup, 1)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # Each step is a bounded sample of the workload, sized so that the W + K steps end within ~100 s on this host:
+    # a 256-locus probe gives the port's rate here, the sample is at most --cpu-sample-loci loci and at least 32.
+    probe = synth.generate(synth.CONFIGS[2], 256, seed=20261018 + 1999, device="cpu").to_host()
+    t0 = time.perf_counter()
+    orc.count_loci(probe.arena, probe.seq_off, probe.lens, probe.est_cn, probe.read_begin, probe.motif_off,
+                   probe.motif_len, n_threads=cores)
+    loci_per_s = probe.n_loci / (time.perf_counter() - t0)
+    n_sample = int(min(args.cpu_sample_loci, max(32, 100.0 * loci_per_s / (steps + warm))))
+    batch = synth.generate(synth.CONFIGS[2], n_sample, seed=20261018 + 2000, device="cpu").to_host()
     times, cells = [], 0.0
     for it in range(warm + steps):
         t0 = time.perf_counter()
