@@ -425,6 +425,9 @@ def main():
             "widening_passes": int(agg["widening_passes"]),
             "reads_packed_kernel": int(agg["reads_packed_kernel"]),
             "reads_general_kernel": int(agg["reads_general_kernel"]),
+            # rank 0's share, like the two counters above (identical reads of a locus run the DP once)
+            "reads_sharing_an_earlier_reads_table": max(0, int(reads_per_step * args.steps - agg["reads_packed_kernel"]
+                                                                - agg["reads_general_kernel"])),
             "parity_sample_bit_exact": parity, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

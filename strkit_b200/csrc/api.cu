@@ -14,6 +14,7 @@
 #include "dp_general.cuh"
 #include "dp_packed.cuh"
 #include "plan.cuh"
+#include "dedupe.cuh"
 #include "int_peak.cuh"
 #include "replay.cuh"
 #include "ref_path.cuh"
@@ -133,6 +134,11 @@ struct strk_batch {
     // host mirror used by the widening passes (per locus, small); per-read planning happens on the device
     std::vector<long long> h_read_begin;
     DevBuf<unsigned char> bin;
+    // identical reads of a locus share one table (dedupe.cuh; STRK_DEDUPE=1): rep[r] = the read whose row r uses
+    DevBuf<unsigned long long> hash;
+    DevBuf<int> rep;
+    int *d_rep = nullptr;
+    long long n_dup = 0;
     int max_n1 = 0, mb_cols_base = 0, mb_m = 0;
     // first-window policy, carried from one block of loci to the next one filled into this object: 1 = short motifs
     // get the wider first window of strk_read_wd (set when a block sent > 2.5 % of its loci to a second pass,
@@ -145,7 +151,7 @@ struct strk_batch {
     void release() {
         arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
         motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
-        bin.release();
+        bin.release(), hash.release(), rep.release();
     }
 };
 
@@ -633,6 +639,8 @@ extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b) {
 static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
     const long long n_reads = b->n_reads, n_loci = b->n_loci;
     cudaStream_t st = ctx->stream;
+    b->d_rep = nullptr;
+    b->n_dup = 0;
     if (n_reads == 0) {
         CU(cudaStreamSynchronize(st));
         return STRK_OK;
@@ -654,6 +662,22 @@ static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
             b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_len, n_reads, arena_bytes,
             ctx->h_consts.packed_ok, b->bin.p, ctx->d_plan);
         CU(cudaGetLastError());
+        // identical reads of a locus share one table (opt-in until validated on the GPU: STRK_DEDUPE=1)
+        const char *dd = getenv("STRK_DEDUPE");
+        if (dd && atoi(dd) != 0 && n_reads > n_loci) {
+            if (b->hash.reserve((size_t)n_reads) != cudaSuccess || b->rep.reserve((size_t)n_reads) != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(STRK_ERR_NOMEM, "batch: cannot allocate the duplicate-read map");
+            }
+            hash_reads_kernel<<<(unsigned)((n_reads * 32 + T - 1) / T), T, 0, st>>>(b->d_arena, b->d_seq_off, b->d_lens, b->d_est,
+                                                                                 n_reads, ctx->d_plan, b->hash.p);
+            CU(cudaGetLastError());
+            dedupe_loci_kernel<<<(unsigned)((n_loci * 32 + T - 1) / T), T, 0, st>>>(b->d_arena, b->d_seq_off, b->d_lens, b->d_est,
+                                                                                  b->d_read_begin, n_loci, b->hash.p, b->bin.p,
+                                                                                  ctx->d_plan, b->rep.p);
+            CU(cudaGetLastError());
+            b->d_rep = b->rep.p;
+        }
         CU(cudaMemcpyAsync(&hp, ctx->d_plan, sizeof(PlanStats), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
@@ -682,9 +706,10 @@ static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
     b->max_n1 = hp.max_n1;
     b->mb_cols_base = hp.mb_cols_base;
     b->mb_m = hp.mb_m;
+    b->n_dup = b->d_rep ? (long long)hp.n_dup : 0;
     CU(cudaMemcpyAsync(ctx->d_bin_off, off, sizeof(off), cudaMemcpyHostToDevice, st));
     plan_reads_scatter_kernel<<<(unsigned)((n_reads + T - 1) / T), T, 0, st>>>(b->bin.p, n_reads, ctx->d_bin_off,
-                                                                              ctx->d_plan, b->d_order);
+                                                                              ctx->d_plan, b->d_order, b->d_rep);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));  // `off` is on this stack frame; the caller's buffers may go away after return
     return STRK_OK;
@@ -698,6 +723,8 @@ static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, c
                            const int32_t *motif_len) {
     const long long n_reads = b->n_reads, n_loci = b->n_loci;
     cudaStream_t st = ctx->stream;
+    b->d_rep = nullptr;  // small batches: every read gets its own table
+    b->n_dup = 0;
     if (n_reads == 0) {
         CU(cudaStreamSynchronize(st));
         return STRK_OK;
@@ -920,7 +947,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         const int threads = 256;
         plan_reads_kernel<<<(unsigned)((n_slots + threads - 1) / threads), threads, 0, st>>>(
             d_read_ids, n_slots, b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_off, b->d_motif_len, wd,
-            ws, W, ctx->fams.p, ctx->d_acc + 1);
+            ws, W, ctx->fams.p, ctx->d_acc + 1, pass == 0 ? b->d_rep : nullptr);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[0], st));
@@ -929,8 +956,9 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         const bool use_packed = kernel != STRK_KERNEL_GENERAL && ctx->h_consts.packed_ok && W <= PK_WINDOW_MAX;
         long long n_packed = 0;
         if (!use_packed) {
-            rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots, b->d_arena, ctx->table.p,
-                                b_len, rowlen, st);
+            // (first pass: the work order lists the representatives only when identical reads share tables)
+            rc = launch_general(ctx, false, ctx->fams.p, pass ? nullptr : b->d_order, n_slots - (pass == 0 ? b->n_dup : 0),
+                                b->d_arena, ctx->table.p, b_len, rowlen, st);
             if (rc) return rc;
         } else {
             // Packed kernel per rows-per-lane class; what it cannot take goes to the general kernel.
@@ -1012,12 +1040,12 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             replay_reads_small_kernel<<<(unsigned)((n_list + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, 0, st>>>(
                 ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
                 b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
-                ctx->d_queue + 1, ctx->d_acc);
+                ctx->d_queue + 1, ctx->d_acc, pass == 0 ? b->d_rep : nullptr);
         else
             replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
                 ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
                 b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
-                ctx->d_queue + 1, ctx->d_acc);
+                ctx->d_queue + 1, ctx->d_acc, pass == 0 ? b->d_rep : nullptr);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[2], st));
@@ -1036,7 +1064,7 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         CU(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
         ms_dp += t0;
         ms_replay += t1;
-        ctx->stats[7] += (double)n_slots;
+        ctx->stats[7] += (double)(n_slots - (pass == 0 ? b->n_dup : 0));  // duplicates run no DP of their own
         if (trace)
             fprintf(stderr, "[strk_batch_run %p] pass %d: wd %d (wide_short %d, %d sizes), %lld reads of %lld loci, %s kernel, "
                     "dp %.3f ms, replay %.3f ms, %u loci left the window, %u used the margin, %u fallbacks\n", (void *)ctx, pass, wd, ws, W,

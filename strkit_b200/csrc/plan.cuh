@@ -16,6 +16,7 @@ struct PlanStats {
     int max_n1;
     int mb_cols_base;  // multi-pass (db > 512) reads: max of max(fl, fr) + m * est
     int mb_m;          //                              max motif length
+    unsigned n_dup;    // reads that share an earlier read's table (dedupe.cuh)
 };
 
 enum PlanError {
@@ -104,20 +105,23 @@ __global__ void plan_reads_scan_kernel(const unsigned long long *__restrict__ se
 }
 
 // segmented work order: class k occupies order[bin_off[k] .. bin_off[k] + bin_cnt[k])
+//   rep != nullptr: reads with rep[r] != r share an earlier read's table and get no work item
 __global__ void plan_reads_scatter_kernel(const unsigned char *__restrict__ bin, long long n_reads,
-                                          const unsigned *__restrict__ bin_off, PlanStats *st, int *__restrict__ order) {
+                                          const unsigned *__restrict__ bin_off, PlanStats *st, int *__restrict__ order,
+                                          const int *__restrict__ rep) {
     __shared__ unsigned s_cnt[STRK_PK_NBIN], s_base[STRK_PK_NBIN];
     if (threadIdx.x < STRK_PK_NBIN) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int b = 0;
     unsigned local = 0;
-    if (r < n_reads) {
+    const bool mine = r < n_reads && (!rep || rep[r] == (int)r);
+    if (mine) {
         b = bin[r];
         local = atomicAdd(&s_cnt[b], 1u);
     }
     __syncthreads();
     if (threadIdx.x < STRK_PK_NBIN && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&st->bin_cursor[threadIdx.x], s_cnt[threadIdx.x]);
     __syncthreads();
-    if (r < n_reads) order[bin_off[b] + s_base[b] + local] = (int)r;
+    if (mine) order[bin_off[b] + s_base[b] + local] = (int)r;
 }

@@ -223,7 +223,8 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
                                     const int *__restrict__ lens, const int *__restrict__ motif_len, int max_iters,
                                     int range, int step, int tie_flags, int *__restrict__ out,
                                     unsigned char *__restrict__ locus_status, unsigned int *miss_count,
-                                    double *ref_cells) {
+                                    double *ref_cells, const int *__restrict__ rep) {
+    // rep != nullptr (first pass only, slot == read): read r looks its scores up in the row of read rep[r]
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_list) return;
     const int locus = locus_ids ? locus_ids[q] : q;
@@ -246,8 +247,8 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
             read_sc += off;  // :1136
         const int n_lo = est - wdr > 0 ? est - wdr : 0;
         const int n_hi = est + wdr;
-        ClimbResult cr =
-            climb_single(table + (size_t)slot * (size_t)W, n_lo, n_hi, read_sc, max_iters, range, step, tie_flags, seen);
+        ClimbResult cr = climb_single(table + (size_t)(rep ? (long long)rep[r] : slot) * (size_t)W, n_lo, n_hi, read_sc,
+                                      max_iters, range, step, tie_flags, seen);
         if (cr.status) {
             status = cr.status;
             break;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(REPLAY_THREADS)
                               const long long *__restrict__ read_begin, const int *__restrict__ est_cn,
                               const int *__restrict__ lens, const int *__restrict__ motif_len, int max_iters, int range,
                               int step, int tie_flags, int *__restrict__ out, unsigned char *__restrict__ locus_status,
-                              unsigned int *miss_count, double *ref_cells) {
+                              unsigned int *miss_count, double *ref_cells, const int *__restrict__ rep) {
     __shared__ int rows[REPLAY_THREADS * (REPLAY_WMAX + 1)];
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_list) return;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(REPLAY_THREADS)
     bool margin_used = false;
     int nrow[REPLAY_WMAX], nest = 0, nl0 = 0, nl1 = 0, nl2 = 0;
     auto fetch = [&](long long r, long long sl) {
-        const int *src = table + (size_t)sl * (size_t)W;
+        const int *src = table + (size_t)(rep ? (long long)rep[r] : sl) * (size_t)W;
 #pragma unroll
         for (int k = 0; k < REPLAY_WMAX; ++k) nrow[k] = k < W ? src[k] : 0;
         nest = est_cn[r];
@@ -345,7 +346,8 @@ __global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_
                                   const unsigned long long *__restrict__ seq_off, const int *__restrict__ lens,
                                   const int *__restrict__ est_cn, const int *__restrict__ read_locus,
                                   const unsigned long long *__restrict__ motif_off, const int *__restrict__ motif_len,
-                                  int wd, int wide_short, int W, FamDesc *__restrict__ fams, double *exec_cells) {
+                                  int wd, int wide_short, int W, FamDesc *__restrict__ fams, double *exec_cells,
+                                  const int *__restrict__ rep) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cells = 0.0;
     if (s < n_slots) {
@@ -365,7 +367,8 @@ __global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_
     f.n_hi = est + wdr;
     fams[s] = f;
     // executed DP cells: one forward sweep over fl + motif*n_hi plus one backward sweep over fr
-    cells = (double)(f.n_fl + f.n_tr + f.n_fr) * ((double)f.n_fl + (double)f.m * (double)f.n_hi + (double)f.n_fr);
+    if (!rep || rep[r] == (int)r)  // a read that shares another read's table executes no cells
+        cells = (double)(f.n_fl + f.n_tr + f.n_fr) * ((double)f.n_fl + (double)f.m * (double)f.n_hi + (double)f.n_fr);
     }
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
     if ((threadIdx.x & 31) == 0 && cells > 0.0) atomicAdd(exec_cells, cells);

@@ -121,7 +121,8 @@ def test_batch_config1_bit_exact(sb, oracle):
     st = eng.stats()
     assert st["reference_cells"] == cells  # the replay scored exactly the sizes the reference scores
     assert 0 < st["executed_cells"] < cells
-    assert st["reads_packed_kernel"] == batch.n_reads  # HiFi reads all take the packed u16x2 kernel
+    # HiFi reads all take the packed u16x2 kernel (identical reads of a locus share one table when STRK_DEDUPE is on)
+    assert st["reads_general_kernel"] == 0 and 0.5 * batch.n_reads < st["reads_packed_kernel"] <= batch.n_reads
     got_general = eng.count_reads(batch, params, kernel=sb.KERNEL_GENERAL)
     assert np.array_equal(got_general, want) and eng.stats()["reads_packed_kernel"] == 0
 
@@ -196,6 +197,39 @@ def test_first_window_policy_changes_passes_not_results(sb, oracle, monkeypatch)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         assert np.array_equal(eng.count_reads(batch, params), want), env
+    eng.close()
+
+
+def test_identical_reads_share_tables(sb, oracle, monkeypatch):
+    """STRK_DEDUPE=1: identical reads of a locus (same flanks, tract, estimate) run the DP once; the replay still runs
+    per read.  HiFi-like blocks (a third of the reads are duplicates), the same sequence with two different estimates,
+    bad estimates that force second passes, and an ONT-like block without duplicates: rows equal the oracle's."""
+    from strkit_b200 import synth
+
+    monkeypatch.setenv("STRK_DEDUPE", "1")
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    for cfg, n_loci, tweak in ((2, 700, None), (2, 700, "est"), (2, 700, "bad"), (3, 300, None)):
+        batch = synth.generate(synth.CONFIGS[cfg], n_loci, seed=40 + cfg).to_host()
+        rng = np.random.default_rng(8)
+        est = batch.est_cn.copy()
+        if tweak == "est":   # same bytes, different start estimate: must not share a table row's window
+            est[rng.random(est.shape[0]) < 0.3] += 1
+        if tweak == "bad":
+            bad = rng.random(est.shape[0]) < 0.05
+            est[bad] = np.maximum(0, est[bad] + rng.integers(-30, 60, int(bad.sum())))
+        batch.est_cn = est.astype(np.int32)
+        got = eng.count_reads(batch, params)
+        want, cells = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
+                                        batch.motif_off, batch.motif_len, n_threads=8)
+        assert np.array_equal(got, want), (cfg, tweak, np.flatnonzero((got != want).any(axis=1))[:10])
+        st = eng.stats()
+        computed = st["reads_packed_kernel"] + st["reads_general_kernel"]
+        if cfg == 2 and tweak is None:
+            assert st["reference_cells"] == cells
+            assert 0.5 * batch.n_reads < computed < 0.8 * batch.n_reads   # ~33 % of the reads share a table
+        if cfg == 3:
+            assert computed >= batch.n_reads                              # nothing to share
     eng.close()
 
 
