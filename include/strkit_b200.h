@@ -60,6 +60,11 @@ typedef struct strk_batch strk_batch;
 /* tie-break switches of the read-path search (0 = the in-tree Python semantics) */
 #define STRK_TIE_WINDOW_LAST 1
 #define STRK_TIE_FINAL_LAST 2
+/* search-policy switches of the same flag word: hypotheses about the Rust body of strkit_rust_ext.get_repeat_count,
+ * which is not in the reference tree (strkit/call/repeat_count_params.py:13: the initial local search range "can be
+ * narrowed within the get_repeat_count fn").  0 = range fixed, as in the in-tree search of repeats.py:100-151. */
+#define STRK_SEARCH_NARROW_FIRST 4 /* range becomes 1 after the first (direction 0) window */
+#define STRK_SEARCH_NARROW_HALVE 8 /* range is halved (not below 1) after every window     */
 
 #define STRK_NSYM 17
 

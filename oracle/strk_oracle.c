@@ -141,6 +141,215 @@ int strk_oracle_sg_align(const char *s1, int n1, const char *s2, int n2, int gap
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * The same alignment vectorised the way parasail's "scan" kernels are (striped query profile built
+ * once per profiled sequence, repeats.py:92-93; per column one pass for the diagonal / horizontal
+ * terms, a prefix scan down the column for the vertical gap, a second pass to apply it), 16-bit
+ * lanes, AVX2.  For the CPU BASELINE only: results are asserted identical to the scalar restatement
+ * above (tests/test_oracle_golden.py) and the parity tests keep using the scalar one unless told
+ * otherwise.  Linear gaps (open == extend, what the reference passes); sequences too long for
+ * 16-bit lanes fall back to the scalar code, as parasail's _sat kernels fall back to wider lanes.
+ * ------------------------------------------------------------------------------------------- */
+#if defined(__AVX2__)
+#include <immintrin.h>
+#define STRK_HAVE_AVX2 1
+#define P16_MAXLEN_OR_0 6400
+#define P16_LANES 16
+#define P16_MAXLEN 6400 /* g * (len + 1) must stay inside int16 for g = 5 */
+
+typedef struct {
+    int n1, seglen;
+    __m256i *prof; /* [17][seglen]: lane l of vector k = score(s1[l * seglen + k], symbol) */
+    __m256i *h, *ht; /* column buffers */
+} prof16;
+
+static void prof16_free(prof16 *p) {
+    if (!p) return;
+    free(p->prof);
+    free(p->h);
+    free(p->ht);
+    free(p);
+}
+
+static prof16 *prof16_create(const char *s1, int n1, const int8_t *matrix) {
+    if (n1 <= 0 || n1 > P16_MAXLEN) return NULL;
+    prof16 *p = (prof16 *)calloc(1, sizeof(prof16));
+    if (!p) return NULL;
+    p->n1 = n1;
+    p->seglen = (n1 + P16_LANES - 1) / P16_LANES;
+    const size_t sl = (size_t)p->seglen;
+    if (posix_memalign((void **)&p->prof, 32, sizeof(__m256i) * sl * STRK_NSYM) ||
+        posix_memalign((void **)&p->h, 32, sizeof(__m256i) * sl) || posix_memalign((void **)&p->ht, 32, sizeof(__m256i) * sl)) {
+        prof16_free(p);
+        return NULL;
+    }
+    int16_t *w = (int16_t *)p->prof;
+    for (int c = 0; c < STRK_NSYM; ++c)
+        for (int k = 0; k < p->seglen; ++k)
+            for (int l = 0; l < P16_LANES; ++l) {
+                int r = l * p->seglen + k;
+                w[((size_t)c * sl + (size_t)k) * P16_LANES + l] =
+                    r < n1 ? matrix[STRK_NSYM * strk_oracle_symbol((unsigned char)s1[r]) + c] : 0;
+            }
+    return p;
+}
+
+/* lanes move up by 1 / 2 / 4 / 8 positions (lane l receives lane l - s); vacated lanes take `fill` */
+static inline __m256i p16_shift1(__m256i v, __m256i fillv) {
+    __m256i t = _mm256_permute2x128_si256(v, v, 0x08);
+    __m256i r = _mm256_alignr_epi8(v, t, 14);
+    return _mm256_blend_epi16(r, fillv, 0x01) /* lane 0 and lane 8 */;
+}
+
+static int sg_align_prof16(const prof16 *p, const char *s2, int n2, int g, int flags, int *score, int *end_query,
+                           int *end_ref) {
+    const int n1 = p->n1, seglen = p->seglen;
+    const int s1_beg = flags & STRK_S1_BEG_FREE, s1_end = flags & STRK_S1_END_FREE;
+    const int s2_beg = flags & STRK_S2_BEG_FREE, s2_end = flags & STRK_S2_END_FREE;
+    __m256i *H = p->h, *Ht = p->ht;
+    int16_t *lastrow = s2_end ? (int16_t *)malloc(sizeof(int16_t) * (size_t)(n2 + 1)) : NULL;
+    if (s2_end && !lastrow) return 2;
+    const int rq = n1 - 1, kq = rq % seglen, lq = rq / seglen; /* position of DP row n1 */
+    const __m256i vg = _mm256_set1_epi16((short)g);
+    const __m256i vneg = _mm256_set1_epi16(-32768);
+    const __m256i vgseg1 = _mm256_set1_epi16((short)(g * seglen > 32767 ? 32767 : g * seglen));
+    /* masks that keep lanes >= s after a lane shift by s (the others are refilled with -32768) */
+    int16_t lane_id[16];
+    for (int l = 0; l < 16; ++l) lane_id[l] = (int16_t)l;
+    const __m256i vlane = _mm256_loadu_si256((const __m256i *)lane_id);
+    /* column 0 */
+    {
+        int16_t *h = (int16_t *)H;
+        for (int k = 0; k < seglen; ++k)
+            for (int l = 0; l < P16_LANES; ++l) {
+                int r = l * seglen + k;
+                h[k * P16_LANES + l] = (int16_t)(s1_beg ? 0 : -g * (r + 1));
+            }
+    }
+    for (int j = 1; j <= n2; ++j) {
+        const __m256i *P = p->prof + (size_t)strk_oracle_symbol((unsigned char)s2[j - 1]) * (size_t)seglen;
+        const int top_prev = s2_beg ? 0 : -g * (j - 1); /* H[0][j-1] */
+        const int top = s2_beg ? 0 : -g * j;            /* H[0][j]   */
+        /* diagonal of vector 0: previous column's last vector moved up one lane, H[0][j-1] into lane 0 */
+        __m256i last = H[seglen - 1];
+        __m256i t = _mm256_permute2x128_si256(last, last, 0x08);
+        __m256i vdiag = _mm256_alignr_epi8(last, t, 14);
+        vdiag = _mm256_insert_epi16(vdiag, (short)top_prev, 0);
+        /* pass 1: diagonal / horizontal terms, and the vertical gap inside each lane's run of rows */
+        __m256i run = vneg;
+        for (int k = 0; k < seglen; ++k) {
+            __m256i hp = H[k];
+            __m256i v = _mm256_max_epi16(_mm256_adds_epi16(vdiag, P[k]), _mm256_subs_epi16(hp, vg));
+            run = _mm256_max_epi16(v, _mm256_subs_epi16(run, vg));
+            Ht[k] = run;
+            vdiag = hp;
+        }
+        /* carry into each lane: value of the row just above its first row.  A[0] = H[0][j], A[l] = lane l-1's last
+         * row (without its own carry); C[l] = max over l' <= l of A[l'] - g * seglen * (l - l') by doubling */
+        __m256i t2 = _mm256_permute2x128_si256(run, run, 0x08);
+        __m256i A = _mm256_alignr_epi8(run, t2, 14);
+        A = _mm256_insert_epi16(A, (short)top, 0);
+        __m256i dec = vgseg1;
+        /* shift by 1 */
+        {
+            __m256i tt = _mm256_permute2x128_si256(A, A, 0x08);
+            __m256i sh = _mm256_alignr_epi8(A, tt, 14);
+            sh = _mm256_blendv_epi8(sh, vneg, _mm256_cmpgt_epi16(_mm256_set1_epi16(1), vlane));
+            A = _mm256_max_epi16(A, _mm256_subs_epi16(sh, dec));
+            dec = _mm256_adds_epi16(dec, dec);
+        }
+        {
+            __m256i tt = _mm256_permute2x128_si256(A, A, 0x08);
+            __m256i sh = _mm256_alignr_epi8(A, tt, 12);
+            sh = _mm256_blendv_epi8(sh, vneg, _mm256_cmpgt_epi16(_mm256_set1_epi16(2), vlane));
+            A = _mm256_max_epi16(A, _mm256_subs_epi16(sh, dec));
+            dec = _mm256_adds_epi16(dec, dec);
+        }
+        {
+            __m256i tt = _mm256_permute2x128_si256(A, A, 0x08);
+            __m256i sh = _mm256_alignr_epi8(A, tt, 8);
+            sh = _mm256_blendv_epi8(sh, vneg, _mm256_cmpgt_epi16(_mm256_set1_epi16(4), vlane));
+            A = _mm256_max_epi16(A, _mm256_subs_epi16(sh, dec));
+            dec = _mm256_adds_epi16(dec, dec);
+        }
+        {
+            __m256i sh = _mm256_permute2x128_si256(A, A, 0x08);
+            sh = _mm256_blendv_epi8(sh, vneg, _mm256_cmpgt_epi16(_mm256_set1_epi16(8), vlane));
+            A = _mm256_max_epi16(A, _mm256_subs_epi16(sh, dec));
+        }
+        /* pass 2: apply the carry down each lane's rows */
+        __m256i c = _mm256_subs_epi16(A, vg);
+        for (int k = 0; k < seglen; ++k) {
+            H[k] = _mm256_max_epi16(Ht[k], c);
+            c = _mm256_subs_epi16(c, vg);
+        }
+        if (lastrow) lastrow[j] = ((const int16_t *)&H[kq])[lq];
+    }
+    int best = NEG_INF, bq = n1 - 1, br = n2 - 1;
+    const int16_t *h = (const int16_t *)H;
+    if (s1_end) {
+        for (int r = 0; r < n1; ++r) {
+            int v = h[(r % seglen) * P16_LANES + r / seglen];
+            if (v > best) best = v, bq = r, br = n2 - 1;
+        }
+    }
+    if (s2_end) {
+        for (int j = 1; j <= n2; ++j)
+            if (lastrow[j] > best) best = lastrow[j], bq = n1 - 1, br = j - 1;
+    }
+    {
+        int corner = h[kq * P16_LANES + lq];
+        if (corner > best || (!s1_end && !s2_end)) best = corner, bq = n1 - 1, br = n2 - 1;
+    }
+    free(lastrow);
+    if (score) *score = best;
+    if (end_query) *end_query = bq;
+    if (end_ref) *end_ref = br;
+    return 0;
+}
+#else
+#define STRK_HAVE_AVX2 0
+#define P16_MAXLEN_OR_0 0
+typedef struct prof16 prof16;
+static void prof16_free(prof16 *p) { (void)p; }
+static prof16 *prof16_create(const char *s1, int n1, const int8_t *matrix) {
+    (void)s1, (void)n1, (void)matrix;
+    return NULL;
+}
+static int sg_align_prof16(const prof16 *p, const char *s2, int n2, int g, int flags, int *score, int *end_query,
+                           int *end_ref) {
+    (void)p, (void)s2, (void)n2, (void)g, (void)flags, (void)score, (void)end_query, (void)end_ref;
+    return 1;
+}
+#endif
+
+/* 1 = the batch / search entry points below align through the AVX2 kernel where it applies (CPU baseline);
+ * 0 (default) = the scalar restatement everywhere (the checker). */
+static int g_use_simd = 0;
+int strk_oracle_set_simd(int on) {
+    int prev = g_use_simd;
+    g_use_simd = on && STRK_HAVE_AVX2;
+    return prev;
+}
+int strk_oracle_have_simd(void) { return STRK_HAVE_AVX2; }
+
+int strk_oracle_sg_align_simd(const char *s1, int n1, const char *s2, int n2, int gap_open, int gap_extend,
+                              const int8_t *matrix, int flags, int *score, int *end_query, int *end_ref) {
+    if (n1 <= 0 || n2 <= 0 || !s1 || !s2 || !matrix) return 1;
+    prof16 *p = (gap_open == gap_extend && n2 <= P16_MAXLEN_OR_0) ? prof16_create(s1, n1, matrix) : NULL;
+    if (!p) return strk_oracle_sg_align(s1, n1, s2, n2, gap_open, gap_extend, matrix, flags, score, end_query, end_ref);
+    int rc = sg_align_prof16(p, s2, n2, gap_open, flags, score, end_query, end_ref);
+    prof16_free(p);
+    return rc;
+}
+
+/* alignment of s2 against an optional prebuilt profile of s1 (NULL, or s2 too long for 16-bit lanes: scalar) */
+static int sg_align_any(const prof16 *p, const char *s1, int n1, const char *s2, int n2, int gap, const int8_t *matrix,
+                        int flags, int *score, int *end_query, int *end_ref) {
+    if (p && n2 > 0 && n2 <= P16_MAXLEN_OR_0) return sg_align_prof16(p, s2, n2, gap, flags, score, end_query, end_ref);
+    return strk_oracle_sg_align(s1, n1, s2, n2, gap, gap, matrix, flags, score, end_query, end_ref);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Candidate construction: f"{flank_left_seq}{motif * n}{flank_right_seq}" scored against the
  * profile of db = fl + tr + fr (the pre-Rust Python body of get_repeat_count; the Rust port is
  * called at repeats.py:58-68).  Mode (free ends) is a parameter: believed plain "sg".
@@ -165,15 +374,21 @@ static char *build_candidate(const char *fl, int n_fl, const char *motif, int m,
     return c;
 }
 
-int strk_oracle_score_candidate(const char *db, int n_db, const char *fl, int n_fl, const char *fr, int n_fr,
-                                const char *motif, int m, int n, int gap, const int8_t *matrix, int flags,
-                                int *score) {
+static int score_candidate_p(const prof16 *p, const char *db, int n_db, const char *fl, int n_fl, const char *fr,
+                             int n_fr, const char *motif, int m, int n, int gap, const int8_t *matrix, int flags,
+                             int *score) {
     int len;
     char *cand = build_candidate(fl, n_fl, motif, m, n, fr, n_fr, 0, &len);
     if (!cand) return 2;
-    int rc = strk_oracle_sg_align(db, n_db, cand, len, gap, gap, matrix, flags, score, NULL, NULL);
+    int rc = sg_align_any(p, db, n_db, cand, len, gap, matrix, flags, score, NULL, NULL);
     free(cand);
     return rc;
+}
+
+int strk_oracle_score_candidate(const char *db, int n_db, const char *fl, int n_fl, const char *fr, int n_fr,
+                                const char *motif, int m, int n, int gap, const int8_t *matrix, int flags,
+                                int *score) {
+    return score_candidate_p(NULL, db, n_db, fl, n_fl, fr, n_fr, motif, m, n, gap, matrix, flags, score);
 }
 
 /* Insertion-ordered int -> value map (Python dict semantics for repeats.py:103-104,154-156). */
@@ -237,6 +452,8 @@ static int get_repeat_count_cells(int start_count, const char *db, int n_db, con
     stack[top++] = (explore_t){start_count + step_size, 1};
     stack[top++] = (explore_t){start_count, 0};
     int n_explored = 0, rc = 0;
+    /* the reference builds the profile of db once per search (profile_create_sat); so does the SIMD baseline */
+    prof16 *prof = g_use_simd ? prof16_create(db, n_db, matrix) : NULL;
 
     while (top > 0 && n_explored < max_iters) {
         explore_t e = stack[--top];
@@ -245,13 +462,17 @@ static int get_repeat_count_cells(int start_count, const char *db, int n_db, con
         int start_size = e.size - ((e.dir < 1 || wide) ? local_search_range : 0);
         if (start_size < 0) start_size = 0;
         int end_size = e.size + ((e.dir > -1 || wide) ? local_search_range : 0);
+        /* Hypotheses about the Rust body (repeat_count_params.py:13: the range "can be narrowed within the
+         * get_repeat_count fn"); 0 = the in-tree statement, where it never changes. */
+        if ((tie_flags & STRK_SEARCH_NARROW_FIRST) && local_search_range > 1) local_search_range = 1;
+        if ((tie_flags & STRK_SEARCH_NARROW_HALVE) && local_search_range > 1) local_search_range /= 2;
 
         int have = 0, mv_size = 0, mv_score = 0;
         for (int i = start_size; i <= end_size; ++i) {
             int idx = omap_find(&seen, i);
             if (idx < 0) {
                 int sc;
-                rc = strk_oracle_score_candidate(db, n_db, fl, n_fl, fr, n_fr, motif, m, i, gap, matrix, flags, &sc);
+                rc = score_candidate_p(prof, db, n_db, fl, n_fl, fr, n_fr, motif, m, i, gap, matrix, flags, &sc);
                 if (rc) goto done;
                 if (cells) *cells += (double)n_db * (double)(n_fl + m * i + n_fr);
                 idx = omap_push(&seen, i, sc, 0, 0, 0);
@@ -293,6 +514,7 @@ static int get_repeat_count_cells(int start_count, const char *db, int n_db, con
 done:
     free(stack);
     omap_free(&seen);
+    prof16_free(prof);
     return rc;
 }
 
@@ -323,20 +545,20 @@ int strk_oracle_get_repeat_count(int start_count, const char *tr, int n_tr, cons
  *   fwd: sg_qe(profile(db), fl + cand)                 -> (score, end_query + 1 - |fl| - ref_size)
  *   rev: sg_qe(profile(db[::-1]), (cand + fr)[::-1])   -> (score, end_query + 1 - |fr| - ref_size)
  * ------------------------------------------------------------------------------------------- */
-static int score_ref_boundaries_rev(const char *db, const char *db_rev, int n_db, const char *fl, int n_fl,
-                                    const char *fr, int n_fr, const char *motif, int m, int n, int ref_size, int gap,
-                                    const int8_t *matrix, int32_t out4[4]) {
+static int score_ref_boundaries_rev(const prof16 *pf, const prof16 *pr, const char *db, const char *db_rev, int n_db,
+                                    const char *fl, int n_fl, const char *fr, int n_fr, const char *motif, int m, int n,
+                                    int ref_size, int gap, const int8_t *matrix, int32_t out4[4]) {
     int len, sc, eq, rc;
     char *ext_r = build_candidate(fl, n_fl, motif, m, n, NULL, 0, 0, &len);
     if (!ext_r) return 2;
-    rc = strk_oracle_sg_align(db, n_db, ext_r, len, gap, gap, matrix, STRK_MODE_SG_QE, &sc, &eq, NULL);
+    rc = sg_align_any(pf, db, n_db, ext_r, len, gap, matrix, STRK_MODE_SG_QE, &sc, &eq, NULL);
     free(ext_r);
     if (rc) return rc;
     out4[0] = sc;
     out4[1] = eq + 1 - n_fl - ref_size;
     char *ext_l = build_candidate(NULL, 0, motif, m, n, fr, n_fr, 1, &len);
     if (!ext_l) return 2;
-    rc = strk_oracle_sg_align(db_rev, n_db, ext_l, len, gap, gap, matrix, STRK_MODE_SG_QE, &sc, &eq, NULL);
+    rc = sg_align_any(pr, db_rev, n_db, ext_l, len, gap, matrix, STRK_MODE_SG_QE, &sc, &eq, NULL);
     free(ext_l);
     if (rc) return rc;
     out4[2] = sc;
@@ -356,7 +578,8 @@ int strk_oracle_score_ref_boundaries(const char *db, int n_db, const char *fl, i
                                      int32_t out4[4]) {
     char *rev = reversed(db, n_db);
     if (!rev) return 2;
-    int rc = score_ref_boundaries_rev(db, rev, n_db, fl, n_fl, fr, n_fr, motif, m, n, ref_size, gap, matrix, out4);
+    int rc = score_ref_boundaries_rev(NULL, NULL, db, rev, n_db, fl, n_fl, fr, n_fr, motif, m, n, ref_size, gap, matrix,
+                                      out4);
     free(rev);
     return rc;
 }
@@ -385,6 +608,8 @@ int strk_oracle_get_ref_repeat_count(int start_count, const char *tr, int n_tr, 
     omap seen; /* v0=fwd score, v1=r_adj, v2=rev score, v3=l_adj (both dicts share their key order, :126-127) */
     memset(&seen, 0, sizeof(seen));
     explore_t *stack = NULL;
+    prof16 *pf = g_use_simd ? prof16_create(db, n_db, matrix) : NULL;     /* :92 */
+    prof16 *pr = g_use_simd ? prof16_create(db_rev, n_db, matrix) : NULL; /* :93 */
 
     if (!respect_coords) { /* :99 */
         int cap = 16, top = 0;
@@ -408,8 +633,8 @@ int strk_oracle_get_ref_repeat_count(int start_count, const char *tr, int n_tr, 
                     int idx = omap_find(&seen, i);
                     if (idx < 0) { /* :123-130 */
                         int32_t r4[4] = {0, 0, 0, 0};
-                        rc = score_ref_boundaries_rev(db, db_rev, n_db, fl, n_fl, fr, n_fr, motif, m, i, ref_size, gap,
-                                                      matrix, r4);
+                        rc = score_ref_boundaries_rev(pf, pr, db, db_rev, n_db, fl, n_fl, fr, n_fr, motif, m, i, ref_size,
+                                                      gap, matrix, r4);
                         if (rc) goto done;
                         idx = omap_push(&seen, i, r4[0], r4[1], r4[2], r4[3]);
                         ++n_offset_scores;
@@ -474,6 +699,8 @@ int strk_oracle_get_ref_repeat_count(int start_count, const char *tr, int n_tr, 
 done:
     free(stack);
     omap_free(&seen);
+    prof16_free(pf);
+    prof16_free(pr);
     free(db);
     free(db_rev);
     return rc;

@@ -41,6 +41,12 @@ extern "C" {
 #define STRK_TIE_WINDOW_LAST 1 /* window max picks the LAST maximal size   */
 #define STRK_TIE_FINAL_LAST 2  /* final pick takes the LAST-inserted max   */
 
+/* Search-policy switches, same flag word (hypotheses about the Rust body; 0 = range fixed as in repeats.py:100-151).
+ * reference strkit/call/repeat_count_params.py:13: initial_local_search_range "can be narrowed within the
+ * get_repeat_count fn". */
+#define STRK_SEARCH_NARROW_FIRST 4 /* range becomes 1 after the first (direction 0) window   */
+#define STRK_SEARCH_NARROW_HALVE 8 /* range is halved (not below 1) after every window       */
+
 #define STRK_NSYM 17 /* 16-letter alphabet + parasail wildcard column      */
 
 /* align_matrix.py:15-44 + iupac.py:9-21: 17x17 substitution matrix, row-major. */
@@ -53,6 +59,15 @@ int strk_oracle_symbol(unsigned char c);
  * Returns 0 on success, non-zero on invalid arguments (empty sequence). */
 int strk_oracle_sg_align(const char *s1, int n1, const char *s2, int n2, int gap_open, int gap_extend,
                          const int8_t *matrix, int flags, int *score, int *end_query, int *end_ref);
+
+/* The same alignment through the AVX2 kernel (16-bit lanes, striped profile + column scan, the layout of
+ * parasail's *_scan_profile kernels); identical results, falls back to the scalar code where it does not apply. */
+int strk_oracle_sg_align_simd(const char *s1, int n1, const char *s2, int n2, int gap_open, int gap_extend,
+                              const int8_t *matrix, int flags, int *score, int *end_query, int *end_ref);
+/* 1: the search / batch entry points below use the AVX2 kernel (the timed CPU baseline); 0 (default): scalar.
+ * Returns the previous setting.  strk_oracle_have_simd: 1 when the library was built with AVX2. */
+int strk_oracle_set_simd(int on);
+int strk_oracle_have_simd(void);
 
 /* Score of candidate fl + motif*n + fr against db = fl + tr + fr (read path). */
 int strk_oracle_score_candidate(const char *db, int n_db, const char *fl, int n_fl, const char *fr, int n_fr,

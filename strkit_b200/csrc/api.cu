@@ -134,7 +134,7 @@ struct strk_batch {
     // host mirror used by the widening passes (per locus, small); per-read planning happens on the device
     std::vector<long long> h_read_begin;
     DevBuf<unsigned char> bin;
-    // identical reads of a locus share one table (dedupe.cuh; STRK_DEDUPE=1): rep[r] = the read whose row r uses
+    // identical reads of a locus share one table (dedupe.cuh): rep[r] = the read whose row r uses
     DevBuf<unsigned long long> hash;
     DevBuf<int> rep;
     int *d_rep = nullptr;
@@ -662,9 +662,9 @@ static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
             b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_len, n_reads, arena_bytes,
             ctx->h_consts.packed_ok, b->bin.p, ctx->d_plan);
         CU(cudaGetLastError());
-        // identical reads of a locus share one table (opt-in until validated on the GPU: STRK_DEDUPE=1)
+        // identical reads of a locus share one table (STRK_DEDUPE=0 switches it off: measurement only)
         const char *dd = getenv("STRK_DEDUPE");
-        if (dd && atoi(dd) != 0 && n_reads > n_loci) {
+        if ((!dd || atoi(dd) != 0) && n_reads > n_loci) {
             if (b->hash.reserve((size_t)n_reads) != cudaSuccess || b->rep.reserve((size_t)n_reads) != cudaSuccess) {
                 cudaGetLastError();
                 return set_err(STRK_ERR_NOMEM, "batch: cannot allocate the duplicate-read map");
@@ -807,7 +807,11 @@ static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, c
     CU(cudaMemcpyAsync(b->d_read_locus, read_locus.data(), (size_t)n_reads * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->d_order, order.data(), (size_t)n_reads * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->bin.p, bin.data(), (size_t)n_reads, cudaMemcpyHostToDevice, st));
-    return STRK_OK;  // pageable sources: the copies above have been staged when the calls return
+    // The caller's arrays (possibly pinned: truly asynchronous DMA) and the vectors above are still being read by the
+    // copies queued on `st`; the header promises that no host pointer is kept after a call returns, and strk_batch_run
+    // may run on a caller stream that is not ordered after `st`.
+    CU(cudaStreamSynchronize(st));
+    return STRK_OK;
 }
 
 // H2D into (possibly recycled) device buffers, then validation + work planning on the device (plan.cuh)

@@ -75,14 +75,20 @@ __host__ __device__ inline ClimbResult climb_single(const int *table, int n_lo, 
     st_size[top] = start_count + step, st_dir[top++] = 1;
     st_size[top] = start_count, st_dir[top++] = 0;
     bool have_best = false;
-    const bool wide = step > range;
+    // Search-policy switches (tie_flags bits 2-3, STRK_SEARCH_* in the header): the Rust body of this search is not in
+    // the reference tree and repeat_count_params.py:13 says the range "can be narrowed within the get_repeat_count
+    // fn".  0 = the in-tree statement (range fixed, repeats.py:100-151); the two narrowing hypotheses only ever shrink
+    // the windows, so the score table of a pass always covers them.
     while (top > 0 && res.n_explored < max_iters) {
         --top;
         const int size = st_size[top], dir = st_dir[top];
         if (size < 0) continue;
+        const bool wide = step > range;
         int start_size = size - ((dir < 1 || wide) ? range : 0);
         if (start_size < 0) start_size = 0;
         const int end_size = size + ((dir > -1 || wide) ? range : 0);
+        if ((tie_flags & 4) && range > 1) range = 1;              // STRK_SEARCH_NARROW_FIRST: after the first window
+        if ((tie_flags & 8) && range > 1) range = range / 2;      // STRK_SEARCH_NARROW_HALVE: after every window
         res.lo_touched = start_size < res.lo_touched ? start_size : res.lo_touched;
         res.hi_touched = end_size > res.hi_touched ? end_size : res.hi_touched;
         bool have = false;

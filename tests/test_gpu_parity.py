@@ -201,12 +201,12 @@ def test_first_window_policy_changes_passes_not_results(sb, oracle, monkeypatch)
 
 
 def test_identical_reads_share_tables(sb, oracle, monkeypatch):
-    """STRK_DEDUPE=1: identical reads of a locus (same flanks, tract, estimate) run the DP once; the replay still runs
+    """Identical reads of a locus (same flanks, tract, estimate) run the DP once; the replay still runs
     per read.  HiFi-like blocks (a third of the reads are duplicates), the same sequence with two different estimates,
     bad estimates that force second passes, and an ONT-like block without duplicates: rows equal the oracle's."""
     from strkit_b200 import synth
 
-    monkeypatch.setenv("STRK_DEDUPE", "1")
+    monkeypatch.delenv("STRK_DEDUPE", raising=False)
     params = sb.RepeatCountParams("repalign", 50, 3, 1)
     eng = sb.Engine()
     for cfg, n_loci, tweak in ((2, 700, None), (2, 700, "est"), (2, 700, "bad"), (3, 300, None)):
@@ -230,6 +230,11 @@ def test_identical_reads_share_tables(sb, oracle, monkeypatch):
             assert 0.5 * batch.n_reads < computed < 0.8 * batch.n_reads   # ~33 % of the reads share a table
         if cfg == 3:
             assert computed >= batch.n_reads                              # nothing to share
+        monkeypatch.setenv("STRK_DEDUPE", "0")                            # measurement switch: every read its own table
+        assert np.array_equal(eng.count_reads(batch, params), want)
+        st = eng.stats()
+        assert st["reads_packed_kernel"] + st["reads_general_kernel"] >= batch.n_reads
+        monkeypatch.delenv("STRK_DEDUPE")
     eng.close()
 
 
@@ -252,7 +257,7 @@ def test_batch_search_parameters(sb, oracle, params):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("tie", [1, 2, 3])
+@pytest.mark.parametrize("tie", [1, 2, 3, 4, 8, 7])
 def test_tie_break_switches(sb, oracle, tie):
     rng = np.random.default_rng(9)
     # homopolymer-ish tracts with wildcards produce many equal scores
@@ -263,6 +268,34 @@ def test_tie_break_switches(sb, oracle, tie):
     want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin,
                                 batch.motif_off, batch.motif_len, tie_flags=tie)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("policy", [4, 8, 5, 10])
+@pytest.mark.parametrize("cfg,search", [(2, (50, 3, 1)), (3, (50, 3, 1)), (3, (30, 7, 2)), (2, (12, 2, 3))])
+def test_search_policy_switches(sb, oracle, policy, cfg, search):
+    """STRK_SEARCH_NARROW_FIRST / _HALVE (with and without a tie switch): the range-narrowing hypotheses about the Rust
+    body of get_repeat_count (repeat_count_params.py:13) are switches of the replay and of the oracle, not assumptions;
+    each one is bit-exact against the oracle run with the same flags, and it changes n_explored on most reads."""
+    from strkit_b200 import synth
+
+    batch = synth.generate(synth.CONFIGS[cfg], 300, seed=77 + cfg).to_host()
+    rng = np.random.default_rng(policy)
+    est = batch.est_cn.copy()
+    off = rng.random(est.shape[0]) < 0.1   # some bad starts: long climbs, iteration budget, second passes
+    est[off] = np.maximum(0, est[off] + rng.integers(-12, 13, int(off.sum())))
+    batch.est_cn = est.astype(np.int32)
+    params = sb.RepeatCountParams("repalign", *search)
+    eng = sb.Engine(tie_flags=policy)
+    got = eng.count_reads(batch, params)
+    want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin, batch.motif_off,
+                                batch.motif_len, max_iters=search[0], local_search_range=search[1], step_size=search[2],
+                                tie_flags=policy, n_threads=8)
+    assert np.array_equal(got, want), np.flatnonzero((got != want).any(axis=1))[:10]
+    base, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin, batch.motif_off,
+                                batch.motif_len, max_iters=search[0], local_search_range=search[1], step_size=search[2],
+                                tie_flags=policy & 3, n_threads=8)
+    assert (want[:, 2] <= base[:, 2]).mean() > 0.95 and (want[:, 2] < base[:, 2]).mean() > 0.5
+    eng.close()
 
 
 def test_long_expansions_multi_pass(sb, oracle):

@@ -157,3 +157,55 @@ def test_locus_memo_equals_per_call_search(oracle):
             assert out[r].tolist() == [n, score, n_explored, start], (l, r)
             frac += delta / max(n, 1)
     assert dup > 0.2 * b.n_reads  # the memo was exercised
+
+
+def _py_search(score, start, max_iters, rng_, step, policy):
+    """Independent pure-Python statement of the single-score search with the range-narrowing hypotheses
+    (flag 4: range -> 1 after the first window; flag 8: range halves after every window); policy 0 is
+    repeats.py:100-156 with one score per size."""
+    to_explore = [(start - step, -1), (start + step, 1), (start, 0)]
+    seen: dict[int, int] = {}
+    n = 0
+    while to_explore and n < max_iters:
+        size, d = to_explore.pop()
+        if size < 0:
+            continue
+        skip = step > rng_
+        lo = max(size - (rng_ if (d < 1 or skip) else 0), 0)
+        hi = size + (rng_ if (d > -1 or skip) else 0)
+        if policy & 4 and rng_ > 1:
+            rng_ = 1
+        if policy & 8 and rng_ > 1:
+            rng_ //= 2
+        szs = []
+        for i in range(lo, hi + 1):
+            if i not in seen:
+                seen[i] = score(i)
+                n += 1
+            szs.append((i, seen[i]))
+        mv = max(szs, key=lambda x: x[1])
+        if mv[0] > size and (new := mv[0] + step) not in seen and new >= 0:
+            to_explore.append((new, 1))
+        if mv[0] < size and (new := mv[0] - step) not in seen and new >= 0:
+            to_explore.append((new, -1))
+    best = max(seen.items(), key=lambda x: x[1])
+    return best, n, best[0] - start
+
+
+@pytest.mark.parametrize("policy", [0, 4, 8])
+def test_search_policy_switches_match_python_statement(oracle, policy):
+    """The narrowing switches of the oracle equal an independent Python statement; a perfect start scores 9 sizes with the
+    in-tree search and 7 with either narrowing hypothesis (range 3, step 1)."""
+    rng = np.random.default_rng(5 + policy)
+    motif, k = "CAG", 20
+    fl = "".join(rng.choice(list("ACGT"), size=70))
+    fr = "".join(rng.choice(list("ACGT"), size=70))
+    tr = motif * k
+    (n, _), n_exp, _ = oracle.get_repeat_count(k, tr, fl, fr, motif, 50, 3, 1, tie_flags=policy)
+    assert (n, n_exp) == (k, 9 if policy == 0 else 7)
+    for start, mi, r_, st in ((k + 10, 50, 3, 1), (k - 9, 50, 3, 1), (k + 40, 30, 7, 2), (k + 5, 50, 8, 1), (k + 20, 50, 1, 4),
+                              (3, 12, 2, 3), (k + 60, 50, 3, 1)):
+        tr2 = tr[:31] + "X" + tr[32:]
+        want = _py_search(lambda i: oracle.score_candidate(tr2, fl, fr, motif, i), start, mi, r_, st, policy)
+        got = oracle.get_repeat_count(start, tr2, fl, fr, motif, mi, r_, st, tie_flags=policy)
+        assert got == want, (start, mi, r_, st)
