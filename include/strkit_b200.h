@@ -117,6 +117,22 @@ int strk_batch_fill(strk_ctx *ctx, strk_batch *batch, const uint8_t *arena, uint
                     const uint64_t *seq_off, const int32_t *lens, const int32_t *est_cn, int64_t n_reads,
                     const int64_t *read_begin, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci);
 
+/* Arena formats.  STRK_ARENA_ASCII: one byte per symbol, as the reference passes its strings.  STRK_ARENA_NIBBLE: two
+ * symbols per byte (low nibble first), code = index into the reference's alphabet "ACGTRYSWKMBDHVNX"
+ * (align_matrix.py:25-26): half the host-to-device bytes of a block.  arena_bytes counts packed bytes; seq_off,
+ * motif_off and lens are in SYMBOLS in both formats.  Bytes outside the 16-letter alphabet (parasail's wildcard
+ * column) have no nibble code: a block that holds one stays ASCII.  The device expands the packed copy (one pass of
+ * 128-bit loads / stores) before any kernel stages a read. */
+#define STRK_ARENA_ASCII 0
+#define STRK_ARENA_NIBBLE 1
+int strk_batch_fill_fmt(strk_ctx *ctx, strk_batch *batch, int arena_format, const uint8_t *arena, uint64_t arena_bytes,
+                        const uint64_t *seq_off, const int32_t *lens, const int32_t *est_cn, int64_t n_reads,
+                        const int64_t *read_begin, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci);
+int strk_count_reads_fmt(strk_ctx *ctx, int arena_format, const uint8_t *arena, uint64_t arena_bytes,
+                         const uint64_t *seq_off, const int32_t *lens, const int32_t *est_cn, int64_t n_reads,
+                         const int64_t *read_begin, const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci,
+                         int max_iters, int local_search_range, int step_size, int kernel, int32_t *out);
+
 /* Run the whole search for a resident batch: score tables (CUDA), exact replay of the reference's
  * hill-climb per locus (CUDA), widening passes for reads whose search left the table window.
  * Results stay on the device.  `stream` is a cudaStream_t (NULL = the context's own stream);
@@ -133,6 +149,15 @@ int strk_count_reads(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, 
                      const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, int max_iters,
                      int local_search_range, int step_size, int kernel, int32_t *out);
+
+/* strkit_rust_ext.get_repeat_count(start_count, tr_seq, flank_left_seq, flank_right_seq, motif, max_iters,
+ * local_search_range, step_size, use_shortcuts=False) (the PyO3 call at strkit/call/repeats.py:58-68), argument for
+ * argument: strings with explicit lengths (no terminator needed), out4 = {best_n, best_score, n_explored,
+ * best_n - start_count} = the ((n, score), n_explored, delta) the reference returns (:55-56).
+ * use_shortcuts != 0 -> STRK_ERR_UNSUPPORTED (the reference always passes False). */
+int strk_get_repeat_count(strk_ctx *ctx, int start_count, const char *tr_seq, int n_tr, const char *flank_left_seq,
+                          int n_fl, const char *flank_right_seq, int n_fr, const char *motif, int m, int max_iters,
+                          int local_search_range, int step_size, int use_shortcuts, int32_t out4[4]);
 
 /* Raw score tables: scores[out_off[r] + (n - n_lo[r])] = alignment score of fl + motif*n + fr vs
  * fl + tr + fr for n in [n_lo[r], n_hi[r]], read r using the motif of locus motif_idx[r]. */

@@ -44,11 +44,16 @@ def _load() -> C.CDLL:
         "strk_batch_upload": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, C.POINTER(_vp)]),
         "strk_batch_create": (C.c_int, [_vp, C.POINTER(_vp)]),
         "strk_batch_fill": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64]),
+        "strk_batch_fill_fmt": (C.c_int, [_vp, _vp, C.c_int, _vp, _u64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64]),
+        "strk_count_reads_fmt": (C.c_int, [_vp, C.c_int, _vp, _u64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, _vp]),
         "strk_batch_run": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
         "strk_batch_download": (C.c_int, [_vp, _vp, _vp]),
         "strk_batch_free": (C.c_int, [_vp, _vp]),
         "strk_count_reads": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
                                        C.c_int, C.c_int, _vp]),
+        "strk_get_repeat_count": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int,
+                                            C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
         "strk_score_tables": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, C.c_int,
                                         _vp]),
         "strk_ref_boundary_tables": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
@@ -70,8 +75,8 @@ def _load() -> C.CDLL:
 
 lib = _load()
 EXPORTED = ("strk_last_error", "strk_version", "strk_device_count", "strk_init", "strk_destroy", "strk_sync", "strk_host_register",
-            "strk_host_unregister", "strk_batch_upload", "strk_batch_create", "strk_batch_fill", "strk_batch_run", "strk_batch_download", "strk_batch_free",
-            "strk_count_reads", "strk_score_tables", "strk_ref_boundary_tables", "strk_ref_counts", "strk_call_alleles", "strk_gmm_fit_counts",
+            "strk_host_unregister", "strk_batch_upload", "strk_batch_create", "strk_batch_fill", "strk_batch_fill_fmt", "strk_count_reads_fmt", "strk_batch_run", "strk_batch_download", "strk_batch_free",
+            "strk_count_reads", "strk_get_repeat_count", "strk_score_tables", "strk_ref_boundary_tables", "strk_ref_counts", "strk_call_alleles", "strk_gmm_fit_counts",
             "strk_alleles_aggregate", "strk_get_stats", "strk_measure_int_peak")
 
 

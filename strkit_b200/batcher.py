@@ -15,7 +15,15 @@ from typing import Iterable, Sequence
 
 import numpy as np
 
-__all__ = ["ReadBatch", "LocusReads", "pack_loci"]
+__all__ = ["ReadBatch", "LocusReads", "pack_loci", "ARENA_ASCII", "ARENA_NIBBLE"]
+
+ARENA_ASCII = 0    # one byte per symbol, as the reference passes its strings
+ARENA_NIBBLE = 1   # two symbols per byte, low nibble first, code = index into "ACGTRYSWKMBDHVNX" (align_matrix.py:25-26)
+_ALPHABET = b"ACGTRYSWKMBDHVNX"
+_NIBBLE_OF = np.full(256, 16, dtype=np.uint8)
+for _i, _c in enumerate(_ALPHABET):
+    _NIBBLE_OF[_c] = _i
+    _NIBBLE_OF[ord(chr(_c).lower())] = _i
 
 
 @dataclass
@@ -37,6 +45,7 @@ class ReadBatch:
     read_begin: np.ndarray   # int64  [n_loci + 1]
     motif_off: np.ndarray    # uint64 [n_loci]
     motif_len: np.ndarray    # int32  [n_loci]
+    arena_format: int = ARENA_ASCII   # ARENA_NIBBLE: `arena` holds two symbols per byte; offsets / lengths stay in symbols
 
     @property
     def n_reads(self) -> int:
@@ -57,12 +66,55 @@ class ReadBatch:
         return int(sum(a.nbytes for a in (self.arena, self.seq_off, self.lens, self.est_cn, self.read_begin,
                                           self.motif_off, self.motif_len)))
 
-    def slice_loci(self, lo: int, hi: int) -> "ReadBatch":
-        """Loci [lo, hi) as their own batch (shares the arena; offsets stay valid)."""
+    def slice_loci(self, lo: int, hi: int, compact: bool = False) -> "ReadBatch":
+        """Loci [lo, hi) as their own batch.  compact=False shares the whole arena (offsets stay valid; cheap, but
+        every call that uploads the slice uploads the whole arena).  compact=True cuts the arena to the slice: the
+        byte range its reads span (reads of consecutive loci are contiguous in every packer of this package) followed by
+        its motifs, offsets rebased -- what a rank of a catalog partition should hold and upload."""
         r0, r1 = int(self.read_begin[lo]), int(self.read_begin[hi])
-        return ReadBatch(self.arena, self.seq_off[r0:r1].copy(), self.lens[r0:r1].copy(), self.est_cn[r0:r1].copy(),
-                         (self.read_begin[lo:hi + 1] - r0).copy(), self.motif_off[lo:hi].copy(),
-                         self.motif_len[lo:hi].copy())
+        if not compact or self.arena_format != ARENA_ASCII:
+            return ReadBatch(self.arena, self.seq_off[r0:r1].copy(), self.lens[r0:r1].copy(), self.est_cn[r0:r1].copy(),
+                             (self.read_begin[lo:hi + 1] - r0).copy(), self.motif_off[lo:hi].copy(),
+                             self.motif_len[lo:hi].copy(), self.arena_format)
+        seq_off, lens = self.seq_off[r0:r1].astype(np.int64), self.lens[r0:r1]
+        if r1 > r0:
+            a0 = int(seq_off.min())
+            a1 = int((seq_off + lens.sum(axis=1, dtype=np.int64)).max())
+        else:
+            a0 = a1 = 0
+        ml = self.motif_len[lo:hi].astype(np.int64)
+        mo = self.motif_off[lo:hi].astype(np.int64)
+        m_new = (a1 - a0) + np.concatenate([[0], np.cumsum(ml)[:-1]]) if hi > lo else np.zeros(0, dtype=np.int64)
+        msrc = np.repeat(mo - m_new, ml) + (a1 - a0) + np.arange(int(ml.sum()), dtype=np.int64) if hi > lo else np.zeros(0, np.int64)
+        arena = np.concatenate([self.arena[a0:a1], self.arena[msrc] if msrc.size else np.zeros(0, np.uint8)])
+        return ReadBatch(arena, (seq_off - a0).astype(np.uint64), lens.copy(), self.est_cn[r0:r1].copy(),
+                         (self.read_begin[lo:hi + 1] - r0).copy(), m_new.astype(np.uint64), self.motif_len[lo:hi].copy())
+
+    def to_ascii(self) -> "ReadBatch":
+        """Inverse of to_nibble (upper-case letters; offsets unchanged)."""
+        if self.arena_format == ARENA_ASCII:
+            return self
+        letters = np.frombuffer(_ALPHABET, dtype=np.uint8)
+        out = np.empty(2 * self.arena.shape[0], dtype=np.uint8)
+        out[0::2] = letters[self.arena & 15]
+        out[1::2] = letters[self.arena >> 4]
+        return ReadBatch(out, self.seq_off, self.lens, self.est_cn, self.read_begin, self.motif_off, self.motif_len,
+                         ARENA_ASCII)
+
+    def to_nibble(self) -> "ReadBatch":
+        """The same batch with a nibble-packed arena (half the host-to-device bytes).  Raises ValueError when the arena
+        holds a byte outside the 16-letter alphabet: parasail's wildcard column has no nibble code, such a block stays
+        ASCII."""
+        if self.arena_format == ARENA_NIBBLE:
+            return self
+        codes = _NIBBLE_OF[self.arena]
+        if codes.size and int(codes.max()) > 15:
+            raise ValueError("arena holds bytes outside ACGTRYSWKMBDHVNX: not representable in the nibble format")
+        if codes.size & 1:
+            codes = np.concatenate([codes, np.zeros(1, dtype=np.uint8)])
+        packed = (codes[0::2] | (codes[1::2] << 4)).astype(np.uint8)
+        return ReadBatch(packed, self.seq_off, self.lens, self.est_cn, self.read_begin, self.motif_off, self.motif_len,
+                         ARENA_NIBBLE)
 
 
 try:  # CPython helper built by __graft_entry__.build() (csrc/fastpack.c): two passes over the objects, no temporaries
@@ -71,21 +123,30 @@ except ImportError:  # not built: the pure-Python body below does the same, ~6x 
     _fastpack = None
 
 
-def pack_loci(loci: Iterable[LocusReads], use_helper: bool = True) -> ReadBatch:
-    """Pack per-locus string tuples into one arena.  With the C helper: one sizing pass and one copying pass over
-    the Python objects.  Without it the per-read Python work is kept to list building done by C-level iterators
-    (zip / chain / map): one str.join + one encode for all sequences, lengths through np.fromiter(map(len, ...)).
+def pack_loci(loci: Iterable[LocusReads], use_helper: bool = True, nibble: bool = False, threads: int = 0) -> ReadBatch:
+    """Pack per-locus string tuples into one arena.  With the C helper (csrc/fastpack.c): one walk over the Python
+    objects under the GIL, then the bytes are moved by `threads` pthreads with the GIL released (0 = one per core, at
+    most 16).  nibble=True emits the ARENA_NIBBLE layout (half the host-to-device bytes); a block holding a byte outside
+    the 16-letter alphabet silently stays ASCII (check .arena_format).  Sequences may be str or bytes.  Without the
+    helper the per-read Python work is kept to list building done by C-level iterators (zip / chain / map).
     (strkit_b200.synth builds fully vectorised synthetic batches.)"""
     from itertools import chain
 
     loci = list(loci)
     if _fastpack is not None and use_helper:
-        arena, seq_off, lens, est, read_begin, motif_off, motif_len = _fastpack.pack(loci)
+        fmt = ARENA_NIBBLE if nibble else ARENA_ASCII
+        try:
+            arena, seq_off, lens, est, read_begin, motif_off, motif_len = _fastpack.pack(loci, nibble, threads)
+        except ValueError as exc:
+            if not nibble or "nibble" not in str(exc):
+                raise
+            fmt = ARENA_ASCII
+            arena, seq_off, lens, est, read_begin, motif_off, motif_len = _fastpack.pack(loci, False, threads)
         return ReadBatch(arena=np.frombuffer(arena, dtype=np.uint8), seq_off=np.frombuffer(seq_off, dtype=np.uint64),
                          lens=np.frombuffer(lens, dtype=np.int32).reshape(-1, 3),
                          est_cn=np.frombuffer(est, dtype=np.int32), read_begin=np.frombuffer(read_begin, dtype=np.int64),
                          motif_off=np.frombuffer(motif_off, dtype=np.uint64),
-                         motif_len=np.frombuffer(motif_len, dtype=np.int32))
+                         motif_len=np.frombuffer(motif_len, dtype=np.int32), arena_format=fmt)
     n_per = []
     for lr in loci:
         n = len(lr.tr_seqs)
@@ -94,11 +155,12 @@ def pack_loci(loci: Iterable[LocusReads], use_helper: bool = True) -> ReadBatch:
         n_per.append(n)
     n_reads = sum(n_per)
     # fl, tr, fr of every read, in read order
-    seqs = list(chain.from_iterable(chain.from_iterable(zip(lr.flank_left_seqs, lr.tr_seqs, lr.flank_right_seqs))
-                                    for lr in loci))
+    _s = lambda x: x.decode("ascii") if isinstance(x, (bytes, bytearray)) else x  # noqa: E731
+    seqs = list(map(_s, chain.from_iterable(chain.from_iterable(zip(lr.flank_left_seqs, lr.tr_seqs, lr.flank_right_seqs))
+                                            for lr in loci)))
     lens_a = np.fromiter(map(len, seqs), dtype=np.int32, count=3 * n_reads).reshape(-1, 3)
     est = np.fromiter(chain.from_iterable(lr.est_cn for lr in loci), dtype=np.int32, count=n_reads)
-    motifs = [lr.motif for lr in loci]
+    motifs = [_s(lr.motif) for lr in loci]
     motif_len = np.fromiter(map(len, motifs), dtype=np.int32, count=len(motifs))
     read_begin = np.zeros(len(loci) + 1, dtype=np.int64)
     np.cumsum(n_per, out=read_begin[1:])
@@ -114,5 +176,11 @@ def pack_loci(loci: Iterable[LocusReads], use_helper: bool = True) -> ReadBatch:
     if len(blob) != seq_bytes + int(motif_len.sum(dtype=np.int64)):
         raise ValueError("pack_loci: sequences must be ASCII")
     arena = np.frombuffer(blob, dtype=np.uint8)
-    return ReadBatch(arena=arena, seq_off=seq_off, lens=lens_a, est_cn=est, read_begin=read_begin, motif_off=motif_off,
-                     motif_len=motif_len)
+    batch = ReadBatch(arena=arena, seq_off=seq_off, lens=lens_a, est_cn=est, read_begin=read_begin, motif_off=motif_off,
+                      motif_len=motif_len)
+    if nibble:
+        try:
+            return batch.to_nibble()
+        except ValueError:
+            pass
+    return batch

@@ -122,6 +122,7 @@ struct strk_ctx {
 struct strk_batch {
     long long n_reads = 0, n_loci = 0;
     DevBuf<unsigned char> arena, status;
+    DevBuf<uint4> arena4;  // nibble-packed copy as uploaded (STRK_ARENA_NIBBLE), expanded into `arena` on the device
     DevBuf<unsigned long long> seq_off, motif_off;
     DevBuf<int> lens, est, motif_len, read_locus, order, out;
     DevBuf<long long> read_begin;
@@ -151,7 +152,7 @@ struct strk_batch {
     void release() {
         arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
         motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
-        bin.release(), hash.release(), rep.release();
+        bin.release(), hash.release(), rep.release(), arena4.release();
     }
 };
 
@@ -817,7 +818,10 @@ static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, c
 // H2D into (possibly recycled) device buffers, then validation + work planning on the device (plan.cuh)
 static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                       const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
-                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci) {
+                      const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci,
+                      int arena_format = STRK_ARENA_ASCII) {
+    if (arena_format != STRK_ARENA_ASCII && arena_format != STRK_ARENA_NIBBLE)
+        return set_err(STRK_ERR_ARG, "batch: unknown arena format %d", arena_format);
     if (n_reads < 0 || n_loci < 0 || n_reads > 0x7ffffff0LL || n_loci > 0x7ffffff0LL)
         return set_err(STRK_ERR_ARG, "batch: bad counts (%lld reads, %lld loci)", (long long)n_reads, (long long)n_loci);
     if ((n_reads && (!arena || !seq_off || !lens || !est_cn)) || !read_begin || (n_loci && (!motif_off || !motif_len)))
@@ -836,7 +840,24 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     cudaError_t e = cudaSuccess;
 #define UP(buf, dst, src, n) \
     if (e == cudaSuccess) e = upload(b->buf, &b->dst, src, (size_t)(n), st)
-    UP(arena, d_arena, (const unsigned char *)arena, arena_bytes);
+    if (arena_format == STRK_ARENA_NIBBLE) {
+        // packed bytes in, byte-per-symbol arena out (offsets and lengths are in symbols either way)
+        const size_t quads = (size_t)((arena_bytes + 15) / 16);
+        e = b->arena4.reserve(quads ? quads : 1);
+        if (e == cudaSuccess) e = b->arena.reserve((size_t)(arena_bytes ? 2 * arena_bytes : 1));
+        b->d_arena = b->arena.p;
+        if (e == cudaSuccess && arena_bytes) {
+            e = cudaMemcpyAsync(b->arena4.p, arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st);
+            const unsigned long long threads = (arena_bytes >> 4) + 1;
+            if (e == cudaSuccess) {
+                expand_nibbles_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(b->arena4.p, arena_bytes, b->arena.p);
+                e = cudaGetLastError();
+            }
+        }
+        arena_bytes *= 2;  // symbols
+    } else {
+        UP(arena, d_arena, (const unsigned char *)arena, arena_bytes);
+    }
     UP(seq_off, d_seq_off, (const unsigned long long *)seq_off, n_reads);
     UP(lens, d_lens, (const int *)lens, 3 * n_reads);
     UP(est, d_est, (const int *)est_cn, n_reads);
@@ -876,6 +897,15 @@ extern "C" int strk_batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *aren
                                int64_t n_loci) {
     if (!ctx || !b) return set_err(STRK_ERR_ARG, "strk_batch_fill: null context/batch");
     return batch_fill(ctx, b, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len, n_loci);
+}
+
+extern "C" int strk_batch_fill_fmt(strk_ctx *ctx, strk_batch *b, int arena_format, const uint8_t *arena,
+                                   uint64_t arena_bytes, const uint64_t *seq_off, const int32_t *lens,
+                                   const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                                   const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci) {
+    if (!ctx || !b) return set_err(STRK_ERR_ARG, "strk_batch_fill_fmt: null context/batch");
+    return batch_fill(ctx, b, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len, n_loci,
+                      arena_format);
 }
 
 extern "C" int strk_batch_upload(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
@@ -1136,20 +1166,57 @@ extern "C" int strk_batch_download(strk_ctx *ctx, strk_batch *b, int32_t *out) {
     return STRK_OK;
 }
 
-extern "C" int strk_count_reads(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
-                                const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
-                                const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, int max_iters,
-                                int local_search_range, int step_size, int kernel, int32_t *out) {
+extern "C" int strk_count_reads_fmt(strk_ctx *ctx, int arena_format, const uint8_t *arena, uint64_t arena_bytes,
+                                    const uint64_t *seq_off, const int32_t *lens, const int32_t *est_cn, int64_t n_reads,
+                                    const int64_t *read_begin, const uint64_t *motif_off, const int32_t *motif_len,
+                                    int64_t n_loci, int max_iters, int local_search_range, int step_size, int kernel,
+                                    int32_t *out) {
     if (!ctx) return set_err(STRK_ERR_ARG, "strk_count_reads: null context");
     if (!ctx->reuse) ctx->reuse = new (std::nothrow) strk_batch();
     if (!ctx->reuse) return set_err(STRK_ERR_NOMEM, "out of host memory");
     strk_batch *b = ctx->reuse;  // device buffers are recycled across calls (no cudaMalloc per block of loci)
     int rc = batch_fill(ctx, b, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin, motif_off, motif_len,
-                        n_loci);
+                        n_loci, arena_format);
     if (rc) return rc;
     rc = strk_batch_run(ctx, b, max_iters, local_search_range, step_size, kernel, nullptr);
     if (!rc) rc = strk_batch_download(ctx, b, out);
     return rc;
+}
+
+extern "C" int strk_count_reads(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                                const int32_t *lens, const int32_t *est_cn, int64_t n_reads, const int64_t *read_begin,
+                                const uint64_t *motif_off, const int32_t *motif_len, int64_t n_loci, int max_iters,
+                                int local_search_range, int step_size, int kernel, int32_t *out) {
+    return strk_count_reads_fmt(ctx, STRK_ARENA_ASCII, arena, arena_bytes, seq_off, lens, est_cn, n_reads, read_begin,
+                                motif_off, motif_len, n_loci, max_iters, local_search_range, step_size, kernel, out);
+}
+
+// The PyO3 function this library replaces, argument for argument (repeats.py:58-68): one read, strings in, four
+// ints out.  A one-read batch through the same machinery (host-side planning, no device planning kernels).
+extern "C" int strk_get_repeat_count(strk_ctx *ctx, int start_count, const char *tr_seq, int n_tr,
+                                     const char *flank_left_seq, int n_fl, const char *flank_right_seq, int n_fr,
+                                     const char *motif, int m, int max_iters, int local_search_range, int step_size,
+                                     int use_shortcuts, int32_t out4[4]) {
+    if (!ctx || !out4 || (n_tr && !tr_seq) || (n_fl && !flank_left_seq) || (n_fr && !flank_right_seq) || !motif)
+        return set_err(STRK_ERR_ARG, "strk_get_repeat_count: null argument");
+    if (n_tr < 0 || n_fl < 0 || n_fr < 0 || m <= 0) return set_err(STRK_ERR_ARG, "strk_get_repeat_count: bad length");
+    if (use_shortcuts)
+        return set_err(STRK_ERR_UNSUPPORTED, "use_shortcuts=True: the reference never passes it (repeats.py:67) and its "
+                                             "semantics are not in the reference tree");
+    std::vector<unsigned char> arena((size_t)n_fl + n_tr + n_fr + m);
+    if (n_fl) memcpy(arena.data(), flank_left_seq, (size_t)n_fl);
+    if (n_tr) memcpy(arena.data() + n_fl, tr_seq, (size_t)n_tr);
+    if (n_fr) memcpy(arena.data() + n_fl + n_tr, flank_right_seq, (size_t)n_fr);
+    memcpy(arena.data() + n_fl + n_tr + n_fr, motif, (size_t)m);
+    const uint64_t seq_off = 0, motif_off = (uint64_t)n_fl + n_tr + n_fr;
+    const int32_t lens[3] = {n_fl, n_tr, n_fr}, est = start_count, mlen = m;
+    const int64_t read_begin[2] = {0, 1};
+    int32_t row[4] = {0, 0, 0, 0};
+    int rc = strk_count_reads_fmt(ctx, STRK_ARENA_ASCII, arena.data(), arena.size(), &seq_off, lens, &est, 1, read_begin,
+                                  &motif_off, &mlen, 1, max_iters, local_search_range, step_size, STRK_KERNEL_AUTO, row);
+    if (rc) return rc;
+    out4[0] = row[0], out4[1] = row[1], out4[2] = row[2], out4[3] = row[0] - start_count;  // repeats.py:55-56
+    return STRK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1403,6 +1470,8 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
+    // counters of this call (strk_get_stats afterwards): the boundary sweeps of phase 1 + the batch runs of phase 2
+    double acc_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const size_t n = (size_t)n_loci;
     const bool timing = getenv("STRK_REF_TIMING") != nullptr;  // coarse phase timers on stderr (tuning only)
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1455,6 +1524,14 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
             CU(cudaGetLastError());
             const int b_len = max_n1 + 2;
             const int rowlen = max_n1 > 32 * 16 ? mb_cols + mb_m * cur_wd + 2 : 2;
+            CU(cudaEventRecord(ctx->ev[0], st));
+            if (d_ids == nullptr) {  // executed cells of the first pass: two sweeps of db x (flank + motif * n_hi)
+                for (int64_t l = 0; l < n_loci; ++l) {
+                    const double n1 = (double)lens[3 * l] + lens[3 * l + 1] + lens[3 * l + 2];
+                    const double hi = (double)start_count[l] + h_wd[(size_t)l];
+                    acc_stats[0] += n1 * ((double)lens[3 * l] + lens[3 * l + 2] + 2.0 * motif_len[l] * hi);
+                }
+            }
             if (d_ids == nullptr && ctx->h_consts.packed_ok && 2 * stride_w <= PK_WINDOW_MAX) {
                 // first pass (locus q = q): packed kernel in reference mode per rows-per-lane class, the forward and
                 // the reverse sg_qe alignment of a locus in the two halves of its lane words; the rest -> general
@@ -1506,15 +1583,24 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
                 rc = launch_general(ctx, true, ctx->fams.p, nullptr, n_pending, d_arena, ctx->table64.p, b_len, rowlen, st);
                 if (rc) return rc;
             }
+            CU(cudaEventRecord(ctx->ev[1], st));
             CU(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned int), st));
             ref_replay1_kernel<<<(unsigned)((n_pending + T - 1) / T), T, 0, st>>>(
                 d_ids, (int)n_pending, ctx->table64.p, ctx->fams.p, d_start, d_rc, d_ref_size, vcf_anchor_size, WD_MAX, d_wd,
                 d_l_off, d_r_off, d_n_off, d_again, d_cnt);
             CU(cudaGetLastError());
+            CU(cudaEventRecord(ctx->ev[2], st));
             ctx->stats[2] += 2;
             unsigned int h_cnt[4] = {0, 0, 0, 0};
             CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            {
+                float t0 = 0.f, t1 = 0.f;
+                CU(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
+                CU(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
+                acc_stats[3] += t0;
+                acc_stats[4] += t1;
+            }
             if (h_cnt[2])
                 return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld left the widest window",
                                (long long)(0x7fffffffu - h_cnt[2]));
@@ -1524,13 +1610,14 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
                                rc_params[3 * l]);
             }
             n_pending = h_cnt[0];
-            ctx->stats[5] += (double)n_pending;
+            acc_stats[5] += (double)n_pending;
             d_ids = d_again;
             d_again = d_again == d_ids_a ? d_ids_b : d_ids_a;
             cur_wd = std::min(WD_MAX, cur_wd * 4);
         }
     }
     const double t_phase1 = now();
+    acc_stats[2] = ctx->stats[2];
     std::vector<int> l_off(n), r_off(n), n_off(n);
     CU(cudaMemcpyAsync(l_off.data(), d_l_off, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(r_off.data(), d_r_off, n * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1592,10 +1679,9 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
         CU(cudaStreamSynchronize(st));  // `ids` is read by the copy above
         rc = batch_plan(ctx, b, arena_bytes);
         if (rc) return rc;
-        const double widened = ctx->stats[5];
         rc = strk_batch_run(ctx, b, tier_key[3 * t], tier_key[3 * t + 1], tier_key[3 * t + 2], STRK_KERNEL_AUTO, nullptr);
         if (rc) return rc;
-        ctx->stats[5] += widened;
+        for (int k = 0; k < 8; ++k) acc_stats[k] += ctx->stats[k];  // strk_batch_run reports its own run only
         res.resize(nt * 4);
         CU(cudaMemcpy(res.data(), b->d_out, nt * 4 * sizeof(int), cudaMemcpyDeviceToHost));
         for (size_t q = 0; q < nt; ++q) {
@@ -1607,9 +1693,11 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
             o[7] = lens[3 * l + 2] - std::max(0, r_off[(size_t)l]);
         }
     }
+    for (int k = 0; k < 8; ++k) ctx->stats[k] = acc_stats[k];
     if (timing)
-        fprintf(stderr, "[strk_ref_counts] %lld loci: upload + phase 1 %.2f ms, phase 2 %.2f ms\n", (long long)n_loci,
-                t_phase1 - t_begin, now() - t_phase1);
+        fprintf(stderr, "[strk_ref_counts] %lld loci: upload + phase 1 %.2f ms, phase 2 %.2f ms (host clock); DP kernels %.2f ms, "
+                "replay kernels %.2f ms (device clock), %d kernels\n", (long long)n_loci, t_phase1 - t_begin, now() - t_phase1,
+                acc_stats[3], acc_stats[4], (int)acc_stats[2]);
     return STRK_OK;
 }
 

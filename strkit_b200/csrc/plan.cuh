@@ -125,3 +125,39 @@ __global__ void plan_reads_scatter_kernel(const unsigned char *__restrict__ bin,
     __syncthreads();
     if (mine) order[bin_off[b] + s_base[b] + local] = (int)r;
 }
+
+// Nibble-packed host arenas (STRK_ARENA_NIBBLE): two symbols per byte, low nibble first, code = index into
+// "ACGTRYSWKMBDHVNX" (align_matrix.py:25-26).  Halves the H2D bytes of a block; this kernel expands the packed copy
+// into the byte-per-symbol arena every DP kernel stages from, right after the copy lands.  One 128-bit load and two
+// 128-bit stores per thread, coalesced; memory-bound (0.45 GB per million reads, < 0.1 ms at HBM speed).
+__global__ void expand_nibbles_kernel(const uint4 *__restrict__ packed, unsigned long long n_bytes,
+                                      unsigned char *__restrict__ out) {
+    __shared__ unsigned char lut[16];
+    if (threadIdx.x < 16) lut[threadIdx.x] = (unsigned char)"ACGTRYSWKMBDHVNX"[threadIdx.x];
+    __syncthreads();
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n_quads = n_bytes >> 4;
+    if (i < n_quads) {
+        const uint4 v = packed[i];
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        unsigned o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned x = w[k] >> (16 * h);
+                o[2 * k + h] = (unsigned)lut[x & 15u] | ((unsigned)lut[(x >> 4) & 15u] << 8) |
+                               ((unsigned)lut[(x >> 8) & 15u] << 16) | ((unsigned)lut[(x >> 12) & 15u] << 24);
+            }
+        }
+        uint4 *dst = (uint4 *)(out + 32ull * i);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else if (i == n_quads) {  // tail: fewer than 16 packed bytes
+        const unsigned char *pb = (const unsigned char *)packed;
+        for (unsigned long long b = n_quads << 4; b < n_bytes; ++b) {
+            out[2 * b] = lut[pb[b] & 15u];
+            out[2 * b + 1] = lut[pb[b] >> 4];
+        }
+    }
+}

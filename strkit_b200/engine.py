@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import os
 import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Iterable, Iterator
@@ -27,6 +28,11 @@ STAT_NAMES = ("executed_cells", "reference_cells", "kernel_launches", "dp_ms", "
 
 def _p(a: np.ndarray) -> int:
     return a.ctypes.data
+
+
+def _ascii_only(batch: ReadBatch) -> None:
+    if batch.arena_format != 0:
+        raise ValueError("this entry point takes ASCII arenas (the nibble format is for the read-path batches)")
 
 
 class DeviceBatch:
@@ -62,6 +68,15 @@ class Engine:
         self._twin: "Engine | None" = None       # second native context on the same GPU (count_reads_stream)
         self._stream_batch = None                # reusable strk_batch of this context
         self._run_lock = threading.Lock()
+        # native contexts are not re-entrant: the per-call drop-in wrappers (which the reference may call from a
+        # multiprocessing.dummy thread pool) hold this lock around their C-ABI calls
+        self.lock = threading.RLock()
+        self.launches = 0    # kernels launched by the streamed path of this context (count_reads_stream accumulates it)
+
+    @property
+    def total_launches(self) -> int:
+        """Kernels launched by count_reads_stream on this GPU so far (both contexts)."""
+        return self.launches + (self._twin.launches if self._twin else 0)
 
     def sync(self) -> None:
         """Wait for everything queued on the context's streams (strk_sync)."""
@@ -90,9 +105,14 @@ class Engine:
     def upload(self, batch: ReadBatch) -> DeviceBatch:
         batch.validate()
         h = C.c_void_p()
-        check(lib.strk_batch_upload(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
-                                    _p(batch.est_cn), batch.n_reads, _p(batch.read_begin), _p(batch.motif_off),
-                                    _p(batch.motif_len), batch.n_loci, C.byref(h)))
+        check(lib.strk_batch_create(self._ctx, C.byref(h)))
+        try:
+            check(lib.strk_batch_fill_fmt(self._ctx, h, batch.arena_format, _p(batch.arena), batch.arena.nbytes,
+                                          _p(batch.seq_off), _p(batch.lens), _p(batch.est_cn), batch.n_reads,
+                                          _p(batch.read_begin), _p(batch.motif_off), _p(batch.motif_len), batch.n_loci))
+        except Exception:
+            lib.strk_batch_free(self._ctx, h)
+            raise
         return DeviceBatch(self, h, batch.n_reads, batch.n_loci)
 
     def run(self, dbatch: DeviceBatch, rc_params: RepeatCountParams, kernel: int = KERNEL_AUTO, stream: int = 0) -> None:
@@ -111,41 +131,55 @@ class Engine:
         batch.validate()
         if out is None:
             out = np.empty((batch.n_reads, 4), dtype=np.int32)
-        check(lib.strk_count_reads(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
-                                   _p(batch.est_cn), batch.n_reads, _p(batch.read_begin), _p(batch.motif_off),
-                                   _p(batch.motif_len), batch.n_loci, rc_params.max_iters,
-                                   rc_params.initial_local_search_range, rc_params.initial_step_size, kernel, _p(out)))
+        check(lib.strk_count_reads_fmt(self._ctx, batch.arena_format, _p(batch.arena), batch.arena.nbytes,
+                                       _p(batch.seq_off), _p(batch.lens), _p(batch.est_cn), batch.n_reads,
+                                       _p(batch.read_begin), _p(batch.motif_off), _p(batch.motif_len), batch.n_loci,
+                                       rc_params.max_iters, rc_params.initial_local_search_range,
+                                       rc_params.initial_step_size, kernel, _p(out)))
         return out
 
     def _stream_step(self, batch: ReadBatch, rc_params: RepeatCountParams, kernel: int, out: np.ndarray,
-                     run_lock: threading.Lock) -> np.ndarray:
+                     run_lock: threading.Lock, ref=None):
         """fill (H2D + device-side planning) -> run (kernels) -> download (D2H) on this context's reusable batch.
-        Only the run phase holds `run_lock`: the copies of one block overlap the kernels of the other context."""
+        Only the run phase holds `run_lock`: the copies of one block overlap the kernels of the other context.
+        ref = (ref_batch, start_count, ref_size, rc[n, 3], vcf_anchor_size, out[n, 8]): the block's reference windows
+        (get_ref_repeat_count, once per locus) go through strk_ref_counts in the same run phase."""
         if self._stream_batch is None:
             h = C.c_void_p()
             check(lib.strk_batch_create(self._ctx, C.byref(h)))
             self._stream_batch = h
-        check(lib.strk_batch_fill(self._ctx, self._stream_batch, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off),
-                                  _p(batch.lens), _p(batch.est_cn), batch.n_reads, _p(batch.read_begin),
-                                  _p(batch.motif_off), _p(batch.motif_len), batch.n_loci))
+        check(lib.strk_batch_fill_fmt(self._ctx, self._stream_batch, batch.arena_format, _p(batch.arena),
+                                      batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens), _p(batch.est_cn), batch.n_reads,
+                                      _p(batch.read_begin), _p(batch.motif_off), _p(batch.motif_len), batch.n_loci))
         with run_lock:
+            if ref is not None:
+                rb, start, ref_size, rc, anchor, ref_out = ref
+                check(lib.strk_ref_counts(self._ctx, _p(rb.arena), rb.arena.nbytes, _p(rb.seq_off), _p(rb.lens), _p(start),
+                                          _p(ref_size), _p(rc), rb.n_loci, _p(rb.motif_off), _p(rb.motif_len), anchor, 0,
+                                          _p(ref_out)))
+                self.launches += int(self.stats()["kernel_launches"])
             check(lib.strk_batch_run(self._ctx, self._stream_batch, rc_params.max_iters,
                                      rc_params.initial_local_search_range, rc_params.initial_step_size, kernel, None))
+            self.launches += int(self.stats()["kernel_launches"])
         check(lib.strk_batch_download(self._ctx, self._stream_batch, _p(out)))
-        return out
+        return out if ref is None else (out, ref[5])
 
     def count_reads_stream(self, batches: Iterable[ReadBatch], rc_params: RepeatCountParams, kernel: int = KERNEL_AUTO,
-                           outs: Iterable[np.ndarray] | None = None) -> Iterator[np.ndarray]:
+                           outs: Iterable[np.ndarray] | None = None, refs: Iterable[tuple] | None = None) -> Iterator:
         """count_reads over a stream of locus blocks (the reference's worker pool consumes the catalog block by
         block, call_sample.py:413-420), results yielded in block order.  Two native contexts on this GPU take
         alternate blocks from two host threads: block i+1 is copied to the device and planned while block i is
         in the DP kernels, so the PCIe copy disappears behind the compute.  Pin the host arrays
-        (strk_host_register / torch pinned memory) or the copies cannot overlap."""
+        (strk_host_register / torch pinned memory) or the copies cannot overlap.
+        refs: per block (ref_batch, start_count int32[n], ref_size int32[n], rc int32[n, 3], vcf_anchor_size,
+        out int32[n, 8]) -- the reference windows of the block's loci (get_ref_repeat_count, call_locus.py:799-810);
+        the stream then yields (reads_out, ref_out) per block: the whole hot path of a block of loci."""
         if self._twin is None:
             d, ef, tf, mat, go, ge = self._init_args
             self._twin = Engine(d, ef, tf, mat, go, ge)
         slots = (self, self._twin)
         out_it = iter(outs) if outs is not None else None
+        ref_it = iter(refs) if refs is not None else None
         pending: collections.deque = collections.deque()
         with ThreadPoolExecutor(max_workers=2, thread_name_prefix="strk-stream") as pool:
             for i, batch in enumerate(batches):
@@ -153,7 +187,8 @@ class Engine:
                     yield pending.popleft().result()
                 batch.validate()
                 out = next(out_it) if out_it is not None else np.empty((batch.n_reads, 4), dtype=np.int32)
-                pending.append(pool.submit(slots[i % 2]._stream_step, batch, rc_params, kernel, out, self._run_lock))
+                ref = next(ref_it) if ref_it is not None else None
+                pending.append(pool.submit(slots[i % 2]._stream_step, batch, rc_params, kernel, out, self._run_lock, ref))
             while pending:
                 yield pending.popleft().result()
 
@@ -161,6 +196,7 @@ class Engine:
     def score_tables(self, batch: ReadBatch, n_lo: np.ndarray, n_hi: np.ndarray, kernel: int = KERNEL_AUTO):
         """Scores of every candidate size in [n_lo[r], n_hi[r]] for every read; returns (scores, out_off)."""
         batch.validate()
+        _ascii_only(batch)
         n_lo = np.ascontiguousarray(n_lo, dtype=np.int32)
         n_hi = np.ascontiguousarray(n_hi, dtype=np.int32)
         width = (n_hi.astype(np.int64) - n_lo + 1)
@@ -177,6 +213,7 @@ class Engine:
         """score_ref_boundaries for a window of sizes; one 'read' (the reference window) per locus.
         Returns (table[k] = (fwd_score, fwd_end_query, rev_score, rev_end_query), out_off)."""
         batch.validate()
+        _ascii_only(batch)
         if batch.n_reads != batch.n_loci:
             raise ValueError("reference batches hold exactly one sequence per locus")
         n_lo = np.ascontiguousarray(n_lo, dtype=np.int32)
@@ -194,6 +231,7 @@ class Engine:
                    respect_coords: bool = False) -> np.ndarray:
         """get_ref_repeat_count for every locus of a reference batch; rc_params int32 [n_loci, 3]."""
         batch.validate()
+        _ascii_only(batch)
         start_count = np.ascontiguousarray(start_count, dtype=np.int32)
         ref_size = np.ascontiguousarray(ref_size, dtype=np.int32)
         rc = np.ascontiguousarray(rc_params, dtype=np.int32).reshape(batch.n_loci, 3)
@@ -217,6 +255,20 @@ class Engine:
 
 _default: dict[tuple[int, int, int], Engine] = {}
 _default_lock = threading.Lock()
+
+
+def _forget_engines_after_fork() -> None:
+    # A CUDA context does not survive fork(): a child (the reference's NonDaemonicPool workers) must build its own
+    # engine.  The parent's handles are dropped without being destroyed -- they are not valid in this process.
+    for eng in _default.values():
+        eng._ctx = None
+        eng._twin = None
+        eng._stream_batch = None
+    _default.clear()
+
+
+if hasattr(os, "register_at_fork"):
+    os.register_at_fork(after_in_child=_forget_engines_after_fork)
 
 
 def default_engine(device: int = 0, end_flags: int = MODE_SG, tie_flags: int = 0) -> Engine:

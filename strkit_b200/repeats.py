@@ -32,7 +32,9 @@ def get_repeat_count(
         raise NotImplementedError("only rc_method='repalign' is implemented (repeats.py:57-68); 'comp' is the "
                                   "experimental composition counter and stays with the reference")
     batch = pack_loci([LocusReads(motif, [start_count], [tr_seq], [flank_left_seq], [flank_right_seq])])
-    out = default_engine().count_reads(batch, rc_params)
+    eng = default_engine()
+    with eng.lock:
+        out = eng.count_reads(batch, rc_params)
     n, score, n_explored, start = (int(v) for v in out[0])
     return (n, score), n_explored, n - start
 
@@ -52,7 +54,9 @@ def get_ref_repeat_count(
     batch = pack_loci([LocusReads(motif, [start_count], [tr_seq], [flank_left_seq], [flank_right_seq])])
     rc = np.array([[rc_params.max_iters, rc_params.initial_local_search_range, rc_params.initial_step_size]],
                   dtype=np.int32)
-    out = default_engine().ref_counts(batch, [start_count], [ref_size], rc, vcf_anchor_size, respect_coords)[0]
+    eng = default_engine()
+    with eng.lock:
+        out = eng.ref_counts(batch, [start_count], [ref_size], rc, vcf_anchor_size, respect_coords)[0]
     cn, score, l_off, r_off, n_off, n_fin, nfl, nfr = (int(v) for v in out)
     db = f"{flank_left_seq}{tr_seq}{flank_right_seq}"
     # the reference returns the adjusted slices without upper-casing them (repeats.py:171-176,190-192)

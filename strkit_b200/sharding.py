@@ -42,10 +42,11 @@ def count_reads_sharded(batch: ReadBatch, compute: Callable[[ReadBatch], np.ndar
                         world_size: int = 1, group=None) -> np.ndarray | None:
     """Run `compute` (e.g. `lambda b: engine.count_reads(b, rc_params)`) on this rank's catalog partition and
     gather the per-read results on rank 0 (returns None on the other ranks).  Every rank holds the same
-    `batch` description (the catalog); only its own partition is touched."""
+    `batch` description (the catalog); only its own partition is touched: the slice handed to `compute` holds the
+    partition's bytes only (slice_loci(compact=True)), so a rank uploads 1/world_size of the arena, not all of it."""
     bounds = partition_catalog(estimated_cost(batch), world_size)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    mine = compute(batch.slice_loci(lo, hi)) if hi > lo else np.zeros((0, 4), dtype=np.int32)
+    mine = compute(batch.slice_loci(lo, hi, compact=True)) if hi > lo else np.zeros((0, 4), dtype=np.int32)
     if world_size == 1:
         return mine
     import torch

@@ -63,16 +63,26 @@ class SynthBatch:
     motif_len: torch.Tensor
     true_cn: torch.Tensor = field(default=None)  # copies actually written into each read (before errors)
 
-    def to_host(self, pin: bool = False) -> ReadBatch:
+    def to_host(self, pin: bool = False, nibble: bool = False) -> ReadBatch:
+        """nibble=True: the arena goes out nibble-packed (batcher.ARENA_NIBBLE), packed on the generating device."""
         def h(t, dt):
             a = t.detach().to("cpu")
             if pin:
                 a = a.pin_memory()
             return a.numpy().view(dt) if dt is not None else a.numpy()
 
-        return ReadBatch(arena=h(self.arena, None), seq_off=h(self.seq_off, np.uint64), lens=h(self.lens, None),
+        arena = self.arena
+        if nibble:
+            lut = torch.full((256,), 16, dtype=torch.uint8, device=arena.device)
+            lut[_ASCII.to(arena.device).long()] = torch.arange(16, dtype=torch.uint8, device=arena.device)
+            codes = lut[arena.long()]
+            if codes.numel() & 1:
+                codes = torch.cat([codes, codes.new_zeros(1)])
+            arena = codes[0::2] | (codes[1::2] << 4)
+        return ReadBatch(arena=h(arena, None), seq_off=h(self.seq_off, np.uint64), lens=h(self.lens, None),
                          est_cn=h(self.est_cn, None), read_begin=h(self.read_begin, None),
-                         motif_off=h(self.motif_off, np.uint64), motif_len=h(self.motif_len, None))
+                         motif_off=h(self.motif_off, np.uint64), motif_len=h(self.motif_len, None),
+                         arena_format=1 if nibble else 0)
 
 
 def _rand_bases(shape, gen, dev):
@@ -217,19 +227,31 @@ def _generate_chunk(spec: SynthSpec, nl: int, gen, dev):
                 motif_len=m.to(torch.int32), true_cn=a.to(torch.int32))
 
 
-# pathogenic-style motifs incl. IUPAC codes (cf. the reference's catalogs/pathogenic_assoc.hg38.tsv)
-EXPANSION_MOTIFS = ["CAG", "CTG", "GAA", "CGG", "GGGGCC", "CCTG", "ATTCT", "TGGAA", "GGCCTG", "CCCCGCCCCGCG",
-                    "RAAAT", "AARRG", "GCN", "CNG", "TTTCA", "AAGGG", "GCC", "CCG", "TTTTA", "GCG"]
+# The motif column of the reference's catalogs/pathogenic_assoc.hg38.tsv, rows 3-46 in file order (44 loci; IUPAC motifs
+# kept as they are: RAAAT, AAAWK, GCN, CASR, ATTTY, AARRG, TTTYA, AARTA, TRC, TRRAA).  BASELINE config 4 = these + 16 resampled.
+PATHOGENIC_MOTIFS = ("RAAAT GCC GGC AAAWK GCC GCN GCA GCA CASR ATTTY CAG AARRG GCC TTTYA GCT TGC GGC GCA GCN AARTA GCCCCG CGG CGG "
+                     "CAG GGC TRC GCG GCG GCG GGC ATTTY TRRAA AGC CTG CCG CGT CAG GGGCCT GCGCGGGGCGGG ATTCT GCA GAGAGG GGC GCC").split()
+EXPANSION_MOTIFS = PATHOGENIC_MOTIFS  # (name kept for callers of the round-1 generator)
+# bases a motif code stands for when a read is synthesised: the reference's own table (strkit/iupac.py:9-21), including its
+# quirk that D lists (A, C, T) like H -- a read base G under a D column would score as a mismatch in the reference too
+IUPAC_BASES = {"R": "AG", "Y": "CT", "S": "CG", "W": "AT", "K": "GT", "M": "AC", "B": "CGT", "D": "ACT", "H": "ACT",
+               "V": "ACG", "N": "ACGT"}
+
+
+def expansion_motifs(n_loci: int, rng) -> list[str]:
+    """The 44 catalog motifs in file order, then motifs resampled from them (44 + 16 for 60 loci)."""
+    extra = [PATHOGENIC_MOTIFS[int(i)] for i in rng.integers(0, len(PATHOGENIC_MOTIFS), max(0, n_loci - len(PATHOGENIC_MOTIFS)))]
+    return (list(PATHOGENIC_MOTIFS) + extra)[:n_loci]
 
 
 def generate_expansions(n_loci: int = 60, reads_per_locus: int = 50, seed: int = 20261018 + 4000,
-                        max_tract: int = 6000, big_lo: int = 200, big_hi: int = 2000):
-    """Config 4: short allele 10-40 copies, expanded allele U{big_lo..big_hi} copies capped at max_tract bases.
-    Small set; per-read numpy.  Returns (ReadBatch, list[LocusReads])."""
+                        max_tract: int = 6000, big_lo: int = 200, big_hi: int = 2000, motifs: list[str] | None = None):
+    """Config 4: short allele 10-40 copies, expanded allele U{big_lo..big_hi} copies capped at max_tract bases, HiFi
+    error channel.  Small set; per-read numpy.  Returns (ReadBatch, list[LocusReads])."""
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
-    iupac = {"R": "AG", "Y": "CT", "S": "CG", "W": "AT", "K": "GT", "M": "AC", "B": "CGT", "D": "AGT", "H": "ACT",
-             "V": "ACG", "N": "ACGT"}
+    iupac = IUPAC_BASES
+    motifs = expansion_motifs(n_loci, rng) if motifs is None else motifs
 
     def channel(seq: np.ndarray) -> np.ndarray:
         u = rng.random(seq.shape[0])
@@ -247,7 +269,7 @@ def generate_expansions(n_loci: int = 60, reads_per_locus: int = 50, seed: int =
 
     loci = []
     for li in range(n_loci):
-        motif = EXPANSION_MOTIFS[li % len(EXPANSION_MOTIFS)]
+        motif = motifs[li % len(motifs)]
         m = len(motif)
         small = int(rng.integers(10, 41))
         big = min(int(rng.integers(big_lo, big_hi + 1)), max_tract // m)

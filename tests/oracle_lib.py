@@ -36,6 +36,8 @@ class Oracle:
         lib.strk_oracle_symbol.argtypes = [C.c_ubyte]
         lib.strk_oracle_sg_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              C.c_int, _i32p, _i32p, _i32p]
+        lib.strk_oracle_sg_align_simd.argtypes = lib.strk_oracle_sg_align.argtypes
+        lib.strk_oracle_set_simd.argtypes = [C.c_int]
         lib.strk_oracle_score_candidate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int,
                                                     C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, _i32p]
         lib.strk_oracle_get_repeat_count.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p,
@@ -57,10 +59,19 @@ class Oracle:
     def symbol(self, ch: str) -> int:
         return self.lib.strk_oracle_symbol(ord(ch))
 
-    def sg_align(self, s1: str, s2: str, flags: int, gap_open: int = GAP, gap_extend: int = GAP):
+    def set_simd(self, on: bool) -> bool:
+        """Route the search / batch entry points through the AVX2 scan kernel (the timed CPU baseline); returns the
+        previous setting.  The checker default is the scalar restatement."""
+        return bool(self.lib.strk_oracle_set_simd(int(on)))
+
+    def have_simd(self) -> bool:
+        return bool(self.lib.strk_oracle_have_simd())
+
+    def sg_align(self, s1: str, s2: str, flags: int, gap_open: int = GAP, gap_extend: int = GAP, simd: bool = False):
         sc, eq, er = C.c_int32(), C.c_int32(), C.c_int32()
         b1, b2 = s1.encode(), s2.encode()
-        rc = self.lib.strk_oracle_sg_align(b1, len(b1), b2, len(b2), gap_open, gap_extend, self.matrix.ctypes.data,
+        fn = self.lib.strk_oracle_sg_align_simd if simd else self.lib.strk_oracle_sg_align
+        rc = fn(b1, len(b1), b2, len(b2), gap_open, gap_extend, self.matrix.ctypes.data,
                                            flags, C.byref(sc), C.byref(eq), C.byref(er))
         if rc:
             raise ValueError(f"oracle sg_align failed: {rc}")

@@ -482,18 +482,20 @@ def test_full_size_catalog_properties(sb, oracle):
     params = sb.RepeatCountParams("repalign", 50, 3, 1)
     eng = sb.Engine()
     rng = np.random.default_rng(4)
-    check_blocks = set(rng.choice(n_blocks, size=6, replace=False).tolist())
+    cut_blocks = set(rng.choice(n_blocks, size=3, replace=False).tolist())
+    oracle.set_simd(True)   # the AVX2 alignments of the CPU port: asserted identical to the scalar ones (test_oracle_golden)
 
     def blocks():
         for i in range(n_blocks):
             sbatch = synth.generate(synth.CONFIGS[2], block, seed=910_000 + i, device="cuda", chunk_loci=4096)
-            hb = sbatch.to_host(pin=True)
+            hb = sbatch.to_host(pin=True, nibble=True)     # what the batcher ships: nibble-packed arenas
             hb.true_cn = sbatch.true_cn.cpu().numpy()
+            lo = int(rng.integers(0, block - 256))
+            hb.check = (lo, sbatch.to_host().slice_loci(lo, lo + 256, compact=True))   # 256 loci of EVERY block
             del sbatch
             yield hb
 
-    kept = {}
-    n_reads = n_equal = 0
+    n_reads = n_equal = n_checked = 0
 
     def tee():
         for i, hb in enumerate(blocks()):
@@ -501,6 +503,7 @@ def test_full_size_catalog_properties(sb, oracle):
             yield hb
 
     stash: list = []
+    kept = {}
     for out in eng.count_reads_stream(tee(), params):
         i, hb = stash.pop(0)
         db_len = hb.lens.sum(axis=1)
@@ -509,21 +512,155 @@ def test_full_size_catalog_properties(sb, oracle):
         assert (np.abs(out[:, 3] - hb.est_cn) <= 64).all()
         n_reads += out.shape[0]
         n_equal += int((out[:, 0] == hb.true_cn).sum())
-        if i in check_blocks:
+        lo, sub = hb.check
+        want, _ = oracle.count_loci(sub.arena, sub.seq_off, sub.lens, sub.est_cn, sub.read_begin, sub.motif_off,
+                                    sub.motif_len, n_threads=16)
+        r0, r1 = int(hb.read_begin[lo]), int(hb.read_begin[lo + 256])
+        assert np.array_equal(out[r0:r1], want), (i, lo)
+        n_checked += r1 - r0
+        if i in cut_blocks:
             kept[i] = (hb, out.copy())
-    assert n_reads == n_blocks * block * 30
+    oracle.set_simd(False)
+    assert n_reads == n_blocks * block * 30 and n_checked == n_blocks * 256 * 30   # 245 760 reads against the CPU port
     assert n_equal / n_reads > 0.97
     torch.cuda.empty_cache()
     for i, (hb, out) in sorted(kept.items()):
-        lo = int(rng.integers(0, block - 96))
-        sub = hb.slice_loci(lo, lo + 96)
-        want, _ = oracle.count_loci(sub.arena, sub.seq_off, sub.lens, sub.est_cn, sub.read_begin, sub.motif_off,
-                                    sub.motif_len, n_threads=8)
-        r0, r1 = int(hb.read_begin[lo]), int(hb.read_begin[lo + 96])
-        assert np.array_equal(out[r0:r1], want), (i, lo)
         # a different cut of the same loci gives the same rows
         cut = int(rng.integers(1, block - 1))
         a, b = hb.slice_loci(0, cut), hb.slice_loci(cut, block)
         again = np.concatenate(list(eng.count_reads_stream([a, b], params)))
         assert np.array_equal(again, out), (i, cut)
+
+
+def test_nibble_arenas_equal_ascii(sb, oracle):
+    """STRK_ARENA_NIBBLE: the nibble-packed host arena (half the H2D bytes) gives the rows of the ASCII one -- blocking
+    call, streamed blocks, resident batch; wildcards, lower case (folded by the packer), odd offsets, tiny batches."""
+    from strkit_b200 import synth
+    from strkit_b200.batcher import LocusReads, pack_loci
+
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    for cfg, n in ((2, 2000), (3, 700)):
+        b = synth.generate(synth.CONFIGS[cfg], n, seed=60 + cfg).to_host()
+        want = eng.count_reads(b, params)
+        nb = b.to_nibble()
+        assert nb.arena.nbytes * 2 - b.arena.nbytes in (0, 1)
+        assert np.array_equal(eng.count_reads(nb, params), want)
+        halves = [nb.slice_loci(0, n // 3), nb.slice_loci(n // 3, n)]
+        assert np.array_equal(np.concatenate(list(eng.count_reads_stream(halves, params))), want)
+        db = eng.upload(nb)
+        eng.run(db, params)
+        assert np.array_equal(eng.download(db), want)
+        db.free()
+    rng = np.random.default_rng(3)
+    loci = [LocusReads("CAG", [4, 5], ["cagCAGXAGCAGC", "CAGCAGNAGCAGCAG"], ["ACGTT", "acgtt"], ["TTGAC", "TTGA"]),
+            LocusReads("AT", [3], ["ATATAT"], ["G"], ["C"])]
+    a, nb = pack_loci(loci), pack_loci(loci, nibble=True)
+    assert nb.arena_format == 1
+    got_a, got_n = eng.count_reads(a, params), eng.count_reads(nb, params)
+    want, _ = oracle.count_loci(a.arena, a.seq_off, a.lens, a.est_cn, a.read_begin, a.motif_off, a.motif_len)
+    assert np.array_equal(got_a, want) and np.array_equal(got_n, want)
+    eng.close()
+
+
+def test_rust_ext_shaped_entry_point(sb, oracle):
+    """strk_get_repeat_count / strkit_rust_ext_shim.get_repeat_count: the 9-argument PyO3 signature of repeats.py:58-68."""
+    from strkit_b200.strkit_rust_ext_shim import get_repeat_count as rust_shaped
+
+    rng = np.random.default_rng(31)
+    for i, (motif, tr, fl, fr) in enumerate(random_families(rng, 60, max_k=30, flank_choices=(5, 20, 70))):
+        start = max(0, round(len(tr) / len(motif)) + int(rng.integers(-4, 5)))
+        mi, r_, st = [(50, 3, 1), (250, 3, 1), (30, 5, 2), (8, 1, 3)][i % 4]
+        assert rust_shaped(start, tr, fl, fr, motif, mi, r_, st) == oracle.get_repeat_count(start, tr, fl, fr, motif, mi, r_, st)
+        assert rust_shaped(start, tr, fl, fr, motif, mi, r_, st, use_shortcuts=False)[1] >= 1
+    with pytest.raises(NotImplementedError):
+        rust_shaped(5, "CAGCAG", "AC", "GT", "CAG", 50, 3, 1, use_shortcuts=True)
+
+
+def test_block_session_equals_per_call_loop(sb, oracle):
+    """Block mode on the GPU: one BlockSession.run() for a block of loci, then the reference's read loop (restated with
+    shims in tests/ref_loop_shim.py) bound to its look-ups, against the same loop making one GPU call per read and
+    against the CPU port: identical read dictionaries and log lines, zero cache misses."""
+    from tests.test_host_cpu import make_block_loci, run_block_vs_per_call
+
+    p = sb.RepeatCountParams("repalign", 50, 3, 1)
+    loci = make_block_loci(seed=9, n_loci=40)
+    sb.get_repeat_count.cache_clear()
+    run_block_vs_per_call(loci, sb.default_engine(), sb.get_repeat_count, p)
+
+    def cpu(start_count, tr_seq, flank_left_seq, flank_right_seq, motif, rc_params):
+        return oracle.get_repeat_count(start_count, tr_seq, flank_left_seq, flank_right_seq, motif, rc_params.max_iters,
+                                       rc_params.initial_local_search_range, rc_params.initial_step_size)
+
+    session = run_block_vs_per_call(loci, sb.default_engine(), cpu, p)
+    # reference windows through the same session
+    rp = sb.get_reference_rc_params("repalign", 20, 250)
+    args = (20, "CAG" * 20, "ACGTTGCATGCATTGACCATGACTGAATCG", "TTGACGATCGGATCGATTAGCTAGCTAAGC", "CAG", 60, 5, rp)
+    session.add_reference(*args)
+    session.run()
+    want = oracle.get_ref_repeat_count(*args[:7], rp.max_iters, rp.initial_local_search_range, rp.initial_step_size)
+    assert session.get_ref_repeat_count(*args) == want and session.ref_misses == 0
+
+
+def test_stream_with_reference_windows(sb):
+    """count_reads_stream(refs=...): a block's reference windows ride in the same run phase; rows equal the separate calls."""
+    from bench import ref_windows_of
+    from strkit_b200 import synth
+
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    blocks = [synth.generate(synth.CONFIGS[2], 900, seed=70 + i).to_host() for i in range(3)]
+    refs = [ref_windows_of(b, np) for b in blocks]
+    want_reads = [eng.count_reads(b, params) for b in blocks]
+    want_refs = [eng.ref_counts(r[0], r[1], r[2], r[3], r[4]) for r in refs]
+    st = eng.stats()
+    assert st["executed_cells"] > 0 and st["dp_ms"] > 0          # strk_ref_counts reports its own counters
+    got = list(eng.count_reads_stream([b.to_nibble() for b in blocks], params, refs=refs))
+    for (reads, ref_out), wr, wf in zip(got, want_reads, want_refs):
+        assert np.array_equal(reads, wr) and np.array_equal(ref_out, wf)
+    eng.close()
+
+
+def test_config4_to_spec_full_search(sb, oracle):
+    """BASELINE config 4 as SURVEY 8d specifies it: motifs of catalogs/pathogenic_assoc.hg38.tsv (IUPAC ones included,
+    reads synthesised with the reference's own IUPAC table), tracts of 3-6 kb, the FULL search of count_reads (not +-1
+    tables) and get_ref_repeat_count with the reference's tiers for large tracts (steps 3 / 5 / 15,
+    repeat_count_params.py:25-35), against the CPU port (AVX2 alignments, asserted identical to the scalar ones)."""
+    from strkit_b200 import synth
+
+    assert len(synth.PATHOGENIC_MOTIFS) == 44 and synth.IUPAC_BASES["D"] == "ACT"
+    motifs = ["RAAAT", "GCN", "AARRG", "CASR", "GCCCCG", "GCGCGGGGCGGG", "CAG", "TRRAA"]
+    batch, loci = synth.generate_expansions(n_loci=8, reads_per_locus=5, seed=77, max_tract=6000, big_lo=600, big_hi=2000,
+                                            motifs=motifs)
+    tract = batch.lens[:, 1]
+    assert tract.max() > 5500 and (tract > 3000).sum() >= 10
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    oracle.set_simd(True)
+    try:
+        got = eng.count_reads(batch, params)
+        want, _ = oracle.count_loci(batch.arena, batch.seq_off, batch.lens, batch.est_cn, batch.read_begin, batch.motif_off,
+                                    batch.motif_len, n_threads=16)
+        assert np.array_equal(got, want), np.flatnonzero((got != want).any(axis=1))[:10]
+        assert eng.stats()["reads_general_kernel"] >= 10
+        # reference windows: the longest read of each of 5 loci stands in for the reference genome, tiers by copy number
+        fams, starts, sizes, rcs = [], [], [], []
+        for lr in loci[:5]:
+            k = int(np.argmax([len(t) for t in lr.tr_seqs]))
+            tr, fl, fr = lr.tr_seqs[k], lr.flank_left_seqs[k], lr.flank_right_seqs[k]
+            est = round(len(tr) / len(lr.motif))
+            p = sb.get_reference_rc_params("repalign", est, 250)
+            fams.append((lr.motif, tr, fl, fr))
+            starts.append(est)
+            sizes.append(len(tr))
+            rcs.append([p.max_iters, p.initial_local_search_range, p.initial_step_size])
+        assert {r[2] for r in rcs} >= {3, 5}      # large-tract tiers exercised
+        rcs[0] = [50, 1, 15]                      # the >= 2000-copy tier (a 6 kb tract holds at most 2000 3-mers)
+        got = eng.ref_counts(families_to_batch(fams), starts, sizes, np.array(rcs), vcf_anchor_size=5)
+        for i, (motif, tr, fl, fr) in enumerate(fams):
+            (cn, score), lo, ro, (n_off, n_fin), (fl2, _, fr2) = oracle.get_ref_repeat_count(
+                starts[i], tr, fl, fr, motif, sizes[i], 5, rcs[i][0], rcs[i][1], rcs[i][2])
+            assert got[i].tolist() == [cn, score, lo, ro, n_off, n_fin, len(fl2), len(fr2)], (i, motif, rcs[i])
+    finally:
+        oracle.set_simd(False)
     eng.close()

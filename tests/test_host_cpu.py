@@ -190,3 +190,176 @@ def test_bench_reference_arm_prints_one_contract_line():
     out = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"),
                          timeout=600)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host batcher: nibble arenas, compact slices, the C packing helper
+# ---------------------------------------------------------------------------------------------------------------
+def _decode(b, off, n):
+    from strkit_b200.batcher import ARENA_NIBBLE
+
+    if b.arena_format == ARENA_NIBBLE:
+        idx = np.arange(off, off + n)
+        byte = b.arena[idx >> 1]
+        return "".join("ACGTRYSWKMBDHVNX"[c] for c in np.where(idx & 1, byte >> 4, byte & 15))
+    return bytes(b.arena[off:off + n]).decode()
+
+
+def test_pack_loci_layouts_agree():
+    """ASCII / nibble, C helper (1 and 3 copy threads) / pure-Python body, str / bytes inputs: the same reads."""
+    from strkit_b200.batcher import LocusReads, pack_loci
+
+    rng = np.random.default_rng(0)
+    loci = []
+    for l in range(300):
+        m = int(rng.integers(1, 7))
+        n = int(rng.integers(0, 6))
+        trs = ["".join(rng.choice(list("ACGTXacgtn"), size=int(rng.integers(0, 40)))) for _ in range(n)]
+        fls = ["".join(rng.choice(list("ACGT"), size=int(rng.integers(0, 9)))) for _ in range(n)]
+        frs = ["".join(rng.choice(list("ACGT"), size=int(rng.integers(0, 9)))) for _ in range(n)]
+        if l % 3 == 0:
+            trs = [t.encode() for t in trs]
+        loci.append(LocusReads("".join(rng.choice(list("ACGTN"), size=m)), [int(rng.integers(0, 30)) for _ in range(n)],
+                               trs, fls, frs))
+    a, p = pack_loci(loci), pack_loci(loci, use_helper=False)
+    for f in ("arena", "seq_off", "lens", "est_cn", "read_begin", "motif_off", "motif_len"):
+        assert np.array_equal(getattr(a, f), getattr(p, f)), f
+    variants = [a, pack_loci(loci, nibble=True, threads=3), pack_loci(loci, nibble=True, threads=1),
+                pack_loci(loci, use_helper=False, nibble=True), a.to_nibble(), a.to_nibble().to_ascii()]
+    assert [v.arena_format for v in variants] == [0, 1, 1, 1, 1, 0]
+    r = 0
+    for l, lr in enumerate(loci):
+        for v in variants:
+            assert _decode(v, int(v.motif_off[l]), int(v.motif_len[l])).upper() == lr.motif.upper()
+        for tr, fl, fr in zip(lr.tr_seqs, lr.flank_left_seqs, lr.flank_right_seqs):
+            want = fl + (tr.decode() if isinstance(tr, bytes) else tr) + fr
+            for v in variants:
+                assert v.lens[r].tolist() == [len(fl), len(tr), len(fr)]
+                assert _decode(v, int(v.seq_off[r]), len(want)).upper() == want.upper()
+            r += 1
+    # a byte outside the 16-letter alphabet has no nibble code: the block stays ASCII
+    assert pack_loci([LocusReads("CAG", [3], ["CAG-AG"], ["AC"], ["GT"])], nibble=True).arena_format == 0
+    with pytest.raises(ValueError):
+        pack_loci([LocusReads("CAG", [3], ["CAG-AG"], ["AC"], ["GT"])]).to_nibble()
+
+
+def test_synth_nibble_and_compact_slices():
+    from strkit_b200 import synth
+
+    b = synth.generate(synth.CONFIGS[2], 60, seed=1).to_host()
+    nb = synth.generate(synth.CONFIGS[2], 60, seed=1).to_host(nibble=True)
+    assert nb.arena_format == 1 and np.array_equal(b.to_nibble().arena, nb.arena)
+    assert np.array_equal(nb.to_ascii().arena[:b.arena.shape[0]], b.arena)
+    full, cut = b.slice_loci(10, 25), b.slice_loci(10, 25, compact=True)
+    assert cut.arena.nbytes < 0.4 * full.arena.nbytes
+    for r in range(cut.n_reads):
+        n = int(cut.lens[r].sum())
+        assert _decode(cut, int(cut.seq_off[r]), n) == _decode(full, int(full.seq_off[r]), n)
+    for l in range(cut.n_loci):
+        assert _decode(cut, int(cut.motif_off[l]), int(cut.motif_len[l])) == _decode(full, int(full.motif_off[l]),
+                                                                                     int(full.motif_len[l]))
+    assert b.slice_loci(7, 7, compact=True).n_reads == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# block mode (strkit_b200.locus_block): host logic, with the device call replaced by the CPU checker
+# ---------------------------------------------------------------------------------------------------------------
+class _CheckerEngine:
+    """Stands in for Engine in CPU tests of the HOST logic: the same calls, answered by the CPU checker."""
+
+    def __init__(self, oracle):
+        import threading
+
+        self.oracle, self.lock, self.calls = oracle, threading.RLock(), 0
+
+    def count_reads(self, batch, rc_params, kernel=0, out=None):
+        self.calls += 1
+        b = batch.to_ascii()
+        return self.oracle.count_loci(b.arena, b.seq_off, b.lens, b.est_cn, b.read_begin, b.motif_off, b.motif_len,
+                                      max_iters=rc_params.max_iters, local_search_range=rc_params.initial_local_search_range,
+                                      step_size=rc_params.initial_step_size)[0]
+
+    def ref_counts(self, batch, start_count, ref_size, rc, vcf_anchor_size, respect_coords=False):
+        self.calls += 1
+        arena = batch.arena.tobytes().decode()
+        out = np.zeros((batch.n_loci, 8), dtype=np.int32)
+        for l in range(batch.n_loci):
+            o, (nfl, ntr, nfr) = int(batch.seq_off[l]), (int(v) for v in batch.lens[l])
+            motif = arena[int(batch.motif_off[l]):int(batch.motif_off[l]) + int(batch.motif_len[l])]
+            (cn, sc), lo, ro, (n_off, n_fin), (fl2, _, fr2) = self.oracle.get_ref_repeat_count(
+                int(start_count[l]), arena[o + nfl:o + nfl + ntr], arena[o:o + nfl], arena[o + nfl + ntr:o + nfl + ntr + nfr],
+                motif, int(ref_size[l]), vcf_anchor_size, int(rc[l][0]), int(rc[l][1]), int(rc[l][2]), respect_coords)
+            out[l] = [cn, sc, lo, ro, n_off, n_fin, len(fl2), len(fr2)]
+        return out
+
+
+def make_block_loci(seed=5, n_loci=24):
+    """Loci for the read-loop comparison: clean reads, reads whose estimate is off (carried offset), junk reads that
+    fail the score filter (one locus with enough of them to be abandoned), a read that exhausts the iteration budget."""
+    from tests.helpers import mutate, rand_seq
+    from tests.ref_loop_shim import SegmentShim
+
+    rng = np.random.default_rng(seed)
+    loci = []
+    for l in range(n_loci):
+        m = int(rng.integers(2, 7))
+        motif = rand_seq(rng, m)
+        k = int(rng.integers(8, 40))
+        fl, fr = rand_seq(rng, 90), rand_seq(rng, 90)
+        segs = []
+        for r in range(int(rng.integers(1, 14))):
+            kk = max(1, k + int(rng.choice([-2, -1, 0, 0, 0, 1, 3])))
+            tr = mutate(rng, motif * kk, 0.01, 0.01, 0.01) or motif
+            if l % 6 == 1 and r % 2 == 0 or (l == 3):
+                tr = rand_seq(rng, len(tr))                       # junk: fails min_read_align_score
+            if l % 8 == 2 and r == 1:
+                tr = motif * kk + rand_seq(rng, 75 * m)           # the length estimate is 75 copies off: iteration budget
+            segs.append(SegmentShim(f"read{l}_{r}", bool(rng.integers(0, 2)), 15000, tr, mutate(rng, fl, 0.01, 0, 0) or "A",
+                                    mutate(rng, fr, 0.01, 0, 0) or "A", m))
+        loci.append((motif, segs))
+    return loci
+
+
+def run_block_vs_per_call(loci, engine, per_call, rc_params):
+    """Block mode (one BlockSession for all loci, then the unchanged loop bound to its look-ups) against per-call mode
+    (the same loop calling `per_call` read by read): read dictionaries and log lines must be identical."""
+    from strkit_b200.locus_block import BlockSession
+    from tests.ref_loop_shim import read_loop
+
+    session = BlockSession(rc_params, engine=engine)
+    for motif, segs in loci:
+        session.add_locus(motif, [(s.get_est_copy_num(), s.tr_seq_wc, s.flank_left_seq_wc, s.flank_right_seq_wc) for s in segs])
+    session.run()
+    n_abandoned = n_budget = 0
+    for motif, segs in loci:
+        want = read_loop(motif, segs, per_call, rc_params)
+        got = read_loop(motif, segs, session.get_repeat_count, rc_params)
+        assert got == want, motif
+        n_abandoned += want[0] is None
+        n_budget += any("maximum # iterations" in ln for ln in want[1])
+    assert session.misses == 0 and session.hits > 0      # the device replayed exactly the calls the loop makes
+    assert n_abandoned >= 1 and n_budget >= 1            # the abort and the budget log line were exercised
+    return session
+
+
+def test_block_session_equals_per_call_loop_host_logic(oracle):
+    from strkit_b200 import RepeatCountParams
+
+    p = RepeatCountParams("repalign", 50, 3, 1)
+
+    def per_call(start_count, tr_seq, flank_left_seq, flank_right_seq, motif, rc_params):
+        return oracle.get_repeat_count(start_count, tr_seq, flank_left_seq, flank_right_seq, motif, rc_params.max_iters,
+                                       rc_params.initial_local_search_range, rc_params.initial_step_size)
+
+    eng = _CheckerEngine(oracle)
+    session = run_block_vs_per_call(make_block_loci(), eng, per_call, p)
+    assert eng.calls == 1                                 # one device call for the whole block
+    # reference windows: warmed the same way; a call that was not collected is a miss (answered per call)
+    from strkit_b200 import get_reference_rc_params
+
+    rp = get_reference_rc_params("repalign", 20, 250)
+    args = (20, "CAG" * 20, "ACGTTGCATGCATTGACCATGACTGAATCG", "TTGACGATCGGATCGATTAGCTAGCTAAGC", "CAG", 60, 5, rp)
+    session.add_reference(*args)
+    session.run()
+    want = oracle.get_ref_repeat_count(*args[:7], rp.max_iters, rp.initial_local_search_range, rp.initial_step_size)
+    assert session.get_ref_repeat_count(*args) == want and session.ref_hits == 1 and session.ref_misses == 0

@@ -209,3 +209,42 @@ def test_search_policy_switches_match_python_statement(oracle, policy):
         want = _py_search(lambda i: oracle.score_candidate(tr2, fl, fr, motif, i), start, mi, r_, st, policy)
         got = oracle.get_repeat_count(start, tr2, fl, fr, motif, mi, r_, st, tie_flags=policy)
         assert got == want, (start, mi, r_, st)
+
+
+def test_simd_baseline_kernel_equals_scalar_restatement(oracle, golden):
+    """The AVX2 scan kernel that the timed CPU baseline uses (16-bit lanes, striped profile, the layout of parasail's
+    *_scan_profile kernels) returns exactly what the scalar restatement returns: raw alignments in all 16 free-end
+    modes (score, end_query, end_ref), the golden get_ref_repeat_count vectors, and a batch of HiFi-like loci."""
+    from strkit_b200 import synth
+
+    assert oracle.have_simd(), "oracle built without AVX2: the CPU baseline would silently be the scalar port"
+    rng = np.random.default_rng(12)
+    for it in range(1500):
+        n1, n2 = int(rng.integers(1, 420)), int(rng.integers(1, 420))
+        alpha = "ACGT" if it % 3 else "ACGTRYSWKMBDHVNXacgtn-"
+        s1 = "".join(rng.choice(list(alpha), size=n1))
+        s2 = "".join(rng.choice(list(alpha), size=n2))
+        if it % 2:  # related sequences: long diagonal runs, gaps
+            s2 = "".join(c for c in s1[int(rng.integers(0, n1)):] if rng.random() > 0.04) or "A"
+        f = int(rng.integers(0, 16))
+        assert oracle.sg_align(s1, s2, f, simd=True) == oracle.sg_align(s1, s2, f), (it, n1, n2, f)
+    long1, long2 = "ACGTT" * 1500, "ACGTT" * 1400 + "GG"          # beyond 16-bit lanes: falls back, same answer
+    assert oracle.sg_align(long1, long2, 15, simd=True) == oracle.sg_align(long1, long2, 15)
+    prev = oracle.set_simd(True)
+    try:
+        for c in golden["ref"]:
+            got = oracle.get_ref_repeat_count(c["start_count"], c["tr_seq"], c["flank_left_seq"], c["flank_right_seq"],
+                                              c["motif"], c["ref_size"], c["vcf_anchor_size"], c["max_iters"],
+                                              c["local_search_range"], c["step_size"], c["respect_coords"])
+            e = c["expect"]
+            assert (got[0][0], got[0][1], got[1], got[2], got[3][0], got[3][1]) == (
+                e["cn"], e["score"], e["l_offset"], e["r_offset"], e["n_offset_scores"], e["n_iters_final"]), c
+        b = synth.generate(synth.CONFIGS[3], 40, seed=5).to_host()
+        fast, cells_fast = oracle.count_loci(b.arena, b.seq_off, b.lens, b.est_cn, b.read_begin, b.motif_off, b.motif_len,
+                                             n_threads=4)
+        oracle.set_simd(False)
+        slow, cells_slow = oracle.count_loci(b.arena, b.seq_off, b.lens, b.est_cn, b.read_begin, b.motif_off, b.motif_len,
+                                             n_threads=4)
+        assert np.array_equal(fast, slow) and cells_fast == cells_slow
+    finally:
+        oracle.set_simd(prev)
