@@ -129,15 +129,45 @@ struct PkState {
     unsigned foff;  // next forward capture slot: uint4 index into the warp's scratch (lane offset applied)
     int cand_stepB;  // the same for the backward half (read mode: one column; reference mode: one per size)
     unsigned boff;
+    unsigned long long pol;  // L2 cache policy of the capture stores (PK_SCRATCH_POLICY bit 1; unused otherwise)
 };
 
 // One column of the wavefront -> scratch: H[0..R) then the prefix-max word, word w of the column at
 // dst[(w / 4) * L].{x,y,z,w}.  Full quads go out as predicated 128-bit stores; the tail (R % 4 cells and the
 // prefix maximum) as 64- / 32-bit pieces, so that no register has to be copied into an aligned quad first.
-__device__ __forceinline__ void pk_st4(unsigned *p, unsigned a, unsigned b, unsigned c, unsigned d, unsigned on) {
+// Capture scratch and L2.  A read's captured columns (~20 KB) are written once, read back once by the combine a few
+// microseconds later and then dead; without a hint every one of those lines is eventually written back to HBM
+// (measured: 1.15 GB of DRAM writes per launch of the R = 10 class against ~35 MB of algorithmic bytes).
+// PK_SCRATCH_POLICY bit 0: after the combine, the lines of the read are DISCARDED (discard.global.L2: their contents
+// are declared dead, so a dirty line is dropped instead of written back); bit 1: the capture stores carry an
+// L2::evict_last policy so the lines outlive the streaming arena traffic until then.
+#ifndef PK_SCRATCH_POLICY
+#define PK_SCRATCH_POLICY 1
+#endif
+__device__ __forceinline__ unsigned long long pk_l2_policy() {
+    unsigned long long pol = 0ull;
+#if PK_SCRATCH_POLICY & 2
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+__device__ __forceinline__ void pk_discard_line(const void *p) {
+#if PK_SCRATCH_POLICY & 1
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+#endif
+}
+__device__ __forceinline__ void pk_st4(unsigned *p, unsigned a, unsigned b, unsigned c, unsigned d, unsigned on,
+                                       unsigned long long pol) {
+    (void)pol;
+#if PK_SCRATCH_POLICY & 2
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %6; }" ::"l"(p),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(on), "l"(pol)
+                 : "memory");
+#else
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"l"(p), "r"(a),
                  "r"(b), "r"(c), "r"(d), "r"(on)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void pk_st2(unsigned *p, unsigned a, unsigned b, unsigned on) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.global.v2.u32 [%0], {%1, %2}; }" ::"l"(p), "r"(a), "r"(b), "r"(on)
@@ -152,7 +182,7 @@ __device__ __forceinline__ void pk_capture(const PkState<R> &st, uint4 *__restri
     constexpr int QF = R / 4, REM = R % 4;  // full quads, cells in the partial one
 #pragma unroll
     for (int q = 0; q < QF; ++q)
-        pk_st4((unsigned *)(dst + q * L), st.H[4 * q], st.H[4 * q + 1], st.H[4 * q + 2], st.H[4 * q + 3], on);
+        pk_st4((unsigned *)(dst + q * L), st.H[4 * q], st.H[4 * q + 1], st.H[4 * q + 2], st.H[4 * q + 3], on, st.pol);
     unsigned *tail = (unsigned *)(dst + QF * L);
     if (REM == 1) {
         pk_st2(tail, st.H[R - 1], st.pm, on);
@@ -476,6 +506,7 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
         st.poff = 0;
         st.foff = (unsigned)lane;
         st.boff = (unsigned)(nW * (QN * L) + lane);
+        st.pol = pk_l2_policy();
 
         // step ranges, common to the units of the warp (their union).  Lane t is at column c during step c + t - 1.
         const int first_cand = f.n_fl + m * a_lo;
@@ -605,6 +636,8 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 }
             }
             __syncwarp();
+            for (int ln = lane; ln < 2 * nW * QN * L / 8; ln += L) pk_discard_line(scr + ln * 8);  // 128-byte lines
+            __syncwarp();
             continue;
         }
         // ---- combine: score(n) for every candidate of the window
@@ -668,6 +701,9 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
                 table[f.out_off + g0 + lane] = best;
             }
         }
+        __syncwarp();
+        // the captured columns of this read are dead: drop their lines from L2 instead of writing them back
+        for (int ln = lane; ln < (nW + 1) * QN * L / 8; ln += L) pk_discard_line(scr + ln * 8);
         __syncwarp();
     }
 }
