@@ -616,6 +616,61 @@ static int launch_packed_classes(strk_ctx *ctx, const int *const *list, const lo
     return STRK_OK;
 }
 
+// One DP pass over a work plan: list[0] = families only the general kernel takes, list[k >= 1] = the packed classes,
+// then the packed kernel's fallbacks (a device-side list) through the general kernel.  The general launch of list[0]
+// is a handful of families (reads / reference windows of 512+ bases, IUPAC reads) whose duration is the LATENCY of one
+// family's dependency chain (0.3 - 0.6 ms) whatever the grid: it starts first, on its own side stream, and runs under
+// the packed launches instead of after them (it used to be 3 % of a 32 768-locus read step and a quarter of the
+// reference path of the same block).
+static int launch_pass(strk_ctx *ctx, const int *const *list, const long long *cnt, const int *flank, const int *mmax,
+                       const int *w_max, long long n_slots, const FamDesc *fams, const unsigned char *arena, void *table,
+                       int b_len, int rowlen, cudaStream_t st, int ref_mode, long long *n_packed) {
+    bool overlap = cnt[0] > 0 && getenv("STRK_GENERAL_SERIAL") == nullptr;  // (the switch: measurement only)
+    long long packed_total = 0;
+    for (int k = 1; k < STRK_PK_NBIN; ++k) {
+        if (!cnt[k]) continue;
+        packed_total += cnt[k];
+        const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], w_max[k]);
+        if (pk_smem_for_class(k, dims) > 200 * 1024) overlap = false;  // that class runs on the general kernel itself
+    }
+    {
+        // scratch of the largest general launch of this pass, reserved before anything is in flight
+        long long fams_max = std::max(cnt[0], std::min(packed_total, (long long)ctx->n_sm * 4));
+        for (int k = 1; k < STRK_PK_NBIN; ++k) fams_max = std::max(fams_max, cnt[k]);
+        const size_t total = ((size_t)b_len + (size_t)GEN_RING * (size_t)rowlen) * (size_t)general_grid(ctx, fams_max);
+        if (ctx->scratch.reserve(total) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of DP scratch", total * sizeof(int));
+        }
+    }
+    int rc = STRK_OK;
+    if (overlap) {
+        if (!ctx->side[0]) CU(cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking));
+        if (!ctx->side_ev[0]) CU(cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
+        if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ctx->fork_ev, st));
+        CU(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0));
+        rc = launch_general(ctx, ref_mode != 0, fams, list[0], cnt[0], arena, table, b_len, rowlen, ctx->side[0]);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->side_ev[0], ctx->side[0]));
+    }
+    rc = launch_packed_classes(ctx, list, cnt, flank, mmax, w_max, n_slots, fams, arena, table, b_len, rowlen, st, ref_mode,
+                               n_packed);
+    if (rc) return rc;
+    if (overlap) {
+        CU(cudaStreamWaitEvent(st, ctx->side_ev[0], 0));
+    } else {
+        rc = launch_general(ctx, ref_mode != 0, fams, list[0], cnt[0], arena, table, b_len, rowlen, st);
+        if (rc) return rc;
+    }
+    if (*n_packed) {
+        rc = launch_general(ctx, ref_mode != 0, fams, ctx->fallback.p, *n_packed, arena, table, b_len, rowlen, st,
+                            ctx->d_queue + 2);
+        if (rc) return rc;
+    }
+    return STRK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // batches
 // ------------------------------------------------------------------------------------------------
@@ -1056,16 +1111,9 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
             int seg_w[STRK_PK_NBIN];
             for (int k = 0; k < STRK_PK_NBIN; ++k) seg_w[k] = (W + 3) / 4 * 4;
-            rc = launch_packed_classes(ctx, seg_list, seg_cnt, seg_flank, seg_mmax, seg_w, n_slots, ctx->fams.p, b->d_arena,
-                                       ctx->table.p, b_len, rowlen, st, 0, &n_packed);
+            rc = launch_pass(ctx, seg_list, seg_cnt, seg_flank, seg_mmax, seg_w, n_slots, ctx->fams.p, b->d_arena, ctx->table.p,
+                             b_len, rowlen, st, 0, &n_packed);
             if (rc) return rc;
-            rc = launch_general(ctx, false, ctx->fams.p, seg_list[0], seg_cnt[0], b->d_arena, ctx->table.p, b_len, rowlen, st);
-            if (rc) return rc;
-            if (n_packed) {
-                rc = launch_general(ctx, false, ctx->fams.p, ctx->fallback.p, n_packed, b->d_arena, ctx->table.p, b_len,
-                                    rowlen, st, ctx->d_queue + 2);
-                if (rc) return rc;
-            }
         }
         CU(cudaEventRecord(ctx->ev[1], st));
         CU(cudaMemsetAsync(ctx->d_queue + 1, 0, sizeof(unsigned int), st));
@@ -1567,17 +1615,9 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
                     seg_cnt[k] = (long long)lists[k].size();
                     seg_w[k] = 2 * stride_w - 1;  // forward + reverse columns of every size of the window
                 }
-                rc = launch_packed_classes(ctx, seg_list, seg_cnt, flank, mmax, seg_w, n_loci, ctx->fams.p, d_arena,
-                                           ctx->table64.p, b_len, rowlen, st, 1, &n_packed);
+                rc = launch_pass(ctx, seg_list, seg_cnt, flank, mmax, seg_w, n_loci, ctx->fams.p, d_arena, ctx->table64.p, b_len,
+                                 rowlen, st, 1, &n_packed);
                 if (rc) return rc;
-                rc = launch_general(ctx, true, ctx->fams.p, d_lists + at[0], (long long)lists[0].size(), d_arena,
-                                    ctx->table64.p, b_len, rowlen, st);
-                if (rc) return rc;
-                if (n_packed) {
-                    rc = launch_general(ctx, true, ctx->fams.p, ctx->fallback.p, n_packed, d_arena, ctx->table64.p, b_len,
-                                        rowlen, st, ctx->d_queue + 2);
-                    if (rc) return rc;
-                }
                 CU(cudaStreamSynchronize(st));  // `flat` is read by the copy above
             } else {
                 rc = launch_general(ctx, true, ctx->fams.p, nullptr, n_pending, d_arena, ctx->table64.p, b_len, rowlen, st);

@@ -58,6 +58,7 @@ struct PassCfg {
 #define GEN_WARPS 4
 #endif
 #define GEN_RING (GEN_WARPS + 1)
+#define GEN_FAST_MMAX 256  // longest motif the steady-state loop of dp_pass takes (longer ones: the general loop only)
 struct GenSync {
     volatile long long progress[GEN_RING];
     unsigned int q;
@@ -85,6 +86,9 @@ struct GenSmem {
     unsigned long long t8[STRK_NSYM_];         // PRMT byte table per column symbol: byte c = score(row class c) + 2g
     unsigned char cls[STRK_SMAT_ROWS + 1];     // row symbol -> PRMT class (A C G T N X other pad), 0x80 = none
     unsigned one;                              // = 1, opaque to the compiler: multiplier of the FMA-pipe adds
+    // byte tables of the motif columns of the sweep in progress, in sweep order (tM[k] = t8[symbol of the k-th column of
+    // a motif copy]): the steady-state loop of dp_pass fetches its column table with one LDS.64 and a wrapping offset
+    unsigned long long tM[2][GEN_FAST_MMAX];  // [1]: the second of two sweeps that run side by side (process_ref_family)
 };
 
 __device__ __forceinline__ int gen_add(int a, int b, unsigned one) {  // a + b as IMAD (FMA pipe)
@@ -98,19 +102,98 @@ __device__ __forceinline__ unsigned gen_prmt(unsigned a, unsigned b, unsigned se
     return r;
 }
 
+// Steady-state steps of a sweep: every lane is inside the matrix, every lane's column is a motif column, and no lane can
+// reach a candidate column -- for a 6 kb expansion that is ~95 % of the steps.  What is left of the general loop's
+// bookkeeping: one LDS.64 of the column's byte table with a wrapping offset, the two shuffles, the boundary-row
+// store of lane 31 and the running maximum of the last row; everything else (column fetch with its flank / motif /
+// reverse cases, activity tests, candidate detection) is compiled out.  TOP / BOT / PM are uniform per strip.
+//   TOP: the strip reads the boundary row of the strip above;  BOT: it publishes its own last row;
+//   PM:  the running maximum of the last row is needed (last strip, free s2 end).
+template <int R, bool TOP, bool BOT, bool PM>
+__device__ __forceinline__ void gen_fast_steps(int (&H)[R], const unsigned (&sel)[R], int &prev_up, int &s, const int s_end,
+                                               const int lane, const unsigned one, const unsigned long long *tM, const int m,
+                                               int koff, int topv, const int tinc, int &top_cur, int &top_nxt,
+                                               const int *__restrict__ top, int *__restrict__ bot, const int ncols,
+                                               volatile long long *prog_in, volatile long long *prog_out,
+                                               const long long stride, const int b, int &pmax, const int g) {
+    const int mbytes = m * 8;
+    const char *tbase = (const char *)tM;
+    int gj = g * (s - lane + 1);  // g * (column of this lane)
+#pragma unroll 1
+    for (; s < s_end; ++s) {
+        int up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
+        if (TOP) {
+            if ((s & 31) == 0) {
+                top_cur = top_nxt;
+                if (s + 33 <= ncols) {
+                    const long long need = (long long)(b - 1) * stride + (s + 64 < ncols ? s + 64 : ncols);
+                    while (*prog_in < need) __nanosleep(40);
+                    __threadfence_block();
+                    if (s + 33 + lane <= ncols) top_nxt = __ldcg(top + s + 33 + lane);
+                }
+            }
+            const int t0 = __shfl_sync(0xffffffffu, top_cur, s & 31);
+            if (lane == 0) up_in = t0;
+        } else {
+            if (lane == 0) up_in = topv;
+            topv += tinc;
+        }
+        const unsigned long long t = *(const unsigned long long *)(tbase + koff);
+        koff += 8;
+        koff = koff == mbytes ? 0 : koff;
+        const unsigned tlo = (unsigned)t, thi = (unsigned)(t >> 32);
+        int d = prev_up, u = up_in;
+        prev_up = up_in;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int left = H[r];
+            const int tt = gen_add(d, (int)gen_prmt(tlo, thi, sel[r]), one);
+            const int h = max(max(tt, u), left);
+            d = left;
+            u = h;
+            H[r] = h;
+        }
+        if (BOT) {
+            if (lane == 31) {
+                const int j = s - 30;
+                bot[j] = H[R - 1];
+                if ((j & 31) == 0) {
+                    __threadfence();
+                    *prog_out = (long long)b * stride + j;
+                }
+            }
+        }
+        if (PM) pmax = max(pmax, H[R - 1] - gj);
+        gj += g;
+    }
+}
+
 // One sweep.  LUT = true: every row symbol of the family is A/C/G/T/N/X/other (or pad) and the score of a cell is a
 // PRMT byte select from the column's 8-byte table (PRMT + IMAD + VIMNMX3 per cell); LUT = false (IUPAC codes inside
 // the read): a shared-memory look-up per cell.
 // Pad rows (front padding) are COPY rows: their score entry is 0 (= -2g + 2g), so with up' >= diag' and
 // up' >= left' each one repeats the value above it; lane 0 of the first strip injects DP row 0 biased as the last
 // pad row (index off), which is what the first real row then reads as its up / diagonal neighbour.
+// Block-level opening of a sweep: the previous sweep of the family is complete, the strip pipeline is reset and the
+// motif's byte tables (sweep order) are in shared memory.  `slot` = which of the two table slots the sweep uses.
+template <bool LUT>
+__device__ __forceinline__ bool dp_pass_open(const PassCfg &c, const GenSmem &sc, GenSync &sy, int slot, bool first) {
+    if (first) {
+        __syncthreads();  // the previous sweep of this family is complete (its B column, its boundary rows)
+        if (threadIdx.x < GEN_RING) sy.progress[threadIdx.x] = -1;
+    }
+    const bool fast_ok = LUT && c.kind != PASS_DUMP && c.m <= GEN_FAST_MMAX;
+    if (fast_ok)
+        for (int k = threadIdx.x; k < c.m; k += blockDim.x)
+            const_cast<GenSmem &>(sc).tM[slot][k] = sc.t8[sc.lut[c.motif[c.rev_motif ? c.m - 1 - k : k]]];
+    return fast_ok;
+}
+
+// `warp` = the (virtual) warp index of the caller within the sweep: warp w takes strips w, w + GEN_WARPS, ...
 template <int R, bool LUT>
-__device__ void dp_pass(const PassCfg &c, const GenSmem &sc, GenSync &sy, int g) {
+__device__ void dp_pass_body(const PassCfg &c, const GenSmem &sc, GenSync &sy, int g, const int warp, const int slot,
+                             const bool fast_ok) {
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    __syncthreads();  // the previous sweep of this family is complete (its B column, its boundary rows)
-    if (threadIdx.x < GEN_RING) sy.progress[threadIdx.x] = -1;
-    __syncthreads();
     const int RB = 32 * R;
     const int NB = c.n1 <= RB ? 1 : (c.n1 + RB - 1) / RB;
     const int off = NB * RB - c.n1;  // number of pad rows in front
@@ -188,7 +271,45 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, GenSync &sy, int g)
         fetch(1 - lane);
         const int row0_bias = g * off;
         const int nsteps = c.ncols + 31;
+        // steady-state range [s_a, s_b): lane 31 is past the prefix columns (s - 30 > n_pre), lane 0 has not reached the
+        // first candidate column n_pre + m * n_lo (it does at step n_pre + m * n_lo - 1)
+        int s_a = c.n_pre + 31, s_b = c.n_pre + c.m * c.n_lo - 1;
+        if (s_b > c.ncols - 1) s_b = c.ncols - 1;
+        if (!fast_ok || s_b - s_a < 64) s_a = s_b = nsteps;  // not worth it: one general loop
         for (int s = 0; s < nsteps; ++s) {
+            if (LUT && s == s_a) {
+                const int koff = ((s - lane - c.n_pre) % c.m) * 8;  // column s - lane + 1 is motif column (j - n_pre - 1) % m
+                const int topv = border_row0(c, s + 1, g) + row0_bias + g * (s + 1);
+                const int tinc = c.s2_beg_free ? g : 0;
+                const bool pm = b == NB - 1;  // (only read there; cheap enough to keep for every last strip)
+#define GEN_FAST(TOPF, BOTF, PMF)                                                                                       \
+    gen_fast_steps<R, TOPF, BOTF, PMF>(H, sel, prev_up, s, s_b, lane, one, sc.tM[slot], c.m, koff, topv, tinc, top_cur, top_nxt, \
+                                       top, bot, c.ncols, prog_in, prog_out, stride, b, pmax, g)
+                if (top) {
+                    if (bot)
+                        GEN_FAST(true, true, false);
+                    else if (pm)
+                        GEN_FAST(true, false, true);
+                    else
+                        GEN_FAST(true, false, false);
+                } else {
+                    if (bot)
+                        GEN_FAST(false, true, false);
+                    else if (pm)
+                        GEN_FAST(false, false, true);
+                    else
+                        GEN_FAST(false, false, false);
+                }
+#undef GEN_FAST
+                // back to the general loop at step s = s_b: restore its one-column-ahead fetch state and the count of
+                // motif copies this lane has completed (last computed column: s - lane)
+                const int jn = s - lane + 1;
+                kk_nxt = (jn - c.n_pre - 1) % c.m;
+                code_nxt = sc.lut[c.motif[c.rev_motif ? c.m - 1 - kk_nxt : kk_nxt]];
+                t_nxt = sc.t8[code_nxt];
+                ncop = (s - lane - c.n_pre) / c.m;
+                if (s >= nsteps) break;
+            }
             const int j = s - lane + 1;
             int up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
             const bool active = j >= 1 && j <= c.ncols;
@@ -296,6 +417,28 @@ __device__ void dp_pass(const PassCfg &c, const GenSmem &sc, GenSync &sy, int g)
     }
 }
 
+template <int R, bool LUT>
+__device__ void dp_pass(const PassCfg &c, const GenSmem &sc, GenSync &sy, int g) {
+    const bool fast_ok = dp_pass_open<LUT>(c, sc, sy, 0, true);
+    __syncthreads();
+    dp_pass_body<R, LUT>(c, sc, sy, g, threadIdx.x >> 5, 0, fast_ok);
+}
+
+// Two independent single-strip sweeps side by side: warp 0 runs `a`, warp 1 runs `b` (the forward and the reverse
+// sg_qe alignment of a reference window).  A one-strip sweep occupies one warp and is bound by the latency of its own
+// dependency chain, so the pair takes the time of one.
+template <int R, bool LUT>
+__device__ void dp_pass_pair(const PassCfg &a, const PassCfg &b, const GenSmem &sc, GenSync &sy, int g) {
+    const bool fa = dp_pass_open<LUT>(a, sc, sy, 0, true);
+    const bool fb = dp_pass_open<LUT>(b, sc, sy, 1, false);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0)
+        dp_pass_body<R, LUT>(a, sc, sy, g, 0, 0, fa);
+    else if (warp == 1)
+        dp_pass_body<R, LUT>(b, sc, sy, g, 0, 1, fb);
+}
+
 // true when every symbol of the family's db has a PRMT row class (no IUPAC code inside the read)
 __device__ inline bool rows_have_classes(const unsigned char *s1, int n1, const GenSmem &sc) {
     bool ok = true;
@@ -401,22 +544,29 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
     c.rev_motif = 0;
     c.ncols = f.n_fl + f.m * f.n_hi;
     c.out64 = out;
+    PassCfg cr = c;
+    cr.pre = arena + f.db_off + f.n_fl + f.n_tr;
+    cr.n_pre = f.n_fr;
+    cr.rev_s1 = 1;
+    cr.rev_pre = 1;
+    cr.rev_motif = 1;
+    cr.ncols = f.n_fr + f.m * f.n_hi;
+    cr.out64 = out + W;
+    if (n1 <= 32 * R && c.ncols > 0 && cr.ncols > 0) {  // one strip each: the two sweeps run on two warps at once
+        if (lut_ok)
+            dp_pass_pair<R, true>(c, cr, sc, sy, g);
+        else
+            dp_pass_pair<R, false>(c, cr, sc, sy, g);
+        return;
+    }
     if (lut_ok)
         dp_pass<R, true>(c, sc, sy, g);
     else
         dp_pass<R, false>(c, sc, sy, g);
-
-    c.pre = arena + f.db_off + f.n_fl + f.n_tr;
-    c.n_pre = f.n_fr;
-    c.rev_s1 = 1;
-    c.rev_pre = 1;
-    c.rev_motif = 1;
-    c.ncols = f.n_fr + f.m * f.n_hi;
-    c.out64 = out + W;
     if (lut_ok)
-        dp_pass<R, true>(c, sc, sy, g);
+        dp_pass<R, true>(cr, sc, sy, g);
     else
-        dp_pass<R, false>(c, sc, sy, g);
+        dp_pass<R, false>(cr, sc, sy, g);
 }
 
 // Persistent kernel: CTAs (GEN_WARPS warps on one family) pull families from a cost-sorted queue.

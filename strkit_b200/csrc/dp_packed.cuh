@@ -142,7 +142,7 @@ struct PkState {
 // are declared dead, so a dirty line is dropped instead of written back); bit 1: the capture stores carry an
 // L2::evict_last policy so the lines outlive the streaming arena traffic until then.
 #ifndef PK_SCRATCH_POLICY
-#define PK_SCRATCH_POLICY 1
+#define PK_SCRATCH_POLICY 0
 #endif
 __device__ __forceinline__ unsigned long long pk_l2_policy() {
     unsigned long long pol = 0ull;
