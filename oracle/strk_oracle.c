@@ -829,3 +829,106 @@ int strk_oracle_count_loci(const char *arena, const uint64_t *seq_off, const int
     free(th);
     return rc;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Soft-clip realignment: parasail.sg_dx_trace_scan_16(ref_window, read, 7, 0, dna_matrix) as
+ * strkit/call/realign.py:56-63 calls it -- s1 = the reference window (aligned end to end, both of its ends
+ * penalised), s2 = the read (both ends free: "d", "x"), affine gaps: a gap of length k costs
+ * open + (k - 1) * extend (7 and 0 there), traceback to a CIGAR that starts at cell (0, 0).
+ *
+ * PARITY UNPINNED: parasail is not in the reference tree.  Restated from the published recurrences (Gotoh, three
+ * states) and parasail's documented result fields; what cannot be checked without the library is a switch:
+ *   STRK_TRACE_OPEN_ON_TIE   a gap state that can be opened or extended at equal score is recorded as opened
+ *                            (default: extended)
+ *   STRK_TRACE_INS_FIRST     equal-scoring predecessors of a cell are tried diagonal, vertical (s1 only, 'I'),
+ *                            horizontal (s2 only, 'D') (default: diagonal, horizontal, vertical)
+ *   STRK_TRACE_END_LAST      the LAST best column of the last row ends the alignment (default: the first)
+ * CIGAR encoding = parasail's / BAM's: (length << 4) | op with M=0 I=1 D=2 '='=7 X=8; 'I' consumes s1 only, 'D' s2 only
+ * (parasail's query = s1); diagonal steps are '=' when the matrix scores the pair > 0, else 'X'.
+ * Returns 0, or 1 bad arguments, 2 out of memory, 4 cigar_cap too small (needed length in *cigar_len).
+ * ------------------------------------------------------------------------------------------- */
+int strk_oracle_realign(const char *s1, int n1, const char *s2, int n2, int gap_open, int gap_extend,
+                        const int8_t *matrix, int trace_flags, int *score, int *end_ref, uint32_t *cigar, int cigar_cap,
+                        int *cigar_len) {
+    if (n1 <= 0 || n2 <= 0 || !s1 || !s2 || !matrix) return 1;
+    const size_t W = (size_t)n2 + 1;
+    int *H = (int *)malloc(sizeof(int) * W), *F = (int *)malloc(sizeof(int) * W);
+    uint8_t *T = (uint8_t *)malloc((size_t)(n1 + 1) * W); /* bits 0-1: H source (0 diag, 1 horizontal, 2 vertical); 2: E extended; 3: F extended */
+    uint8_t *c2 = (uint8_t *)malloc((size_t)n2);
+    if (!H || !F || !T || !c2) {
+        free(H), free(F), free(T), free(c2);
+        return 2;
+    }
+    for (int j = 0; j < n2; ++j) c2[j] = (uint8_t)strk_oracle_symbol((unsigned char)s2[j]);
+    const int open_tie = trace_flags & 1, ins_first = trace_flags & 2, end_last = trace_flags & 4;
+    for (int j = 0; j <= n2; ++j) H[j] = 0, F[j] = NEG_INF; /* s2 begin free: row 0 is all zero */
+    for (int i = 1; i <= n1; ++i) {
+        const int8_t *mrow = matrix + STRK_NSYM * strk_oracle_symbol((unsigned char)s1[i - 1]);
+        int diag = H[0];
+        int left = -gap_open - (i - 1) * gap_extend; /* H[i][0]: s1 begin penalised */
+        int E = NEG_INF;
+        H[0] = left;
+        T[(size_t)i * W] = 2; /* column 0: vertical */
+        for (int j = 1; j <= n2; ++j) {
+            const int up = H[j];
+            uint8_t t = 0;
+            const int e_opn = left - gap_open, e_ext = E - gap_extend;
+            if (e_ext > e_opn || (e_ext == e_opn && !open_tie)) E = e_ext, t |= 4; else E = e_opn;
+            const int f_opn = up - gap_open, f_ext = F[j] - gap_extend;
+            if (f_ext > f_opn || (f_ext == f_opn && !open_tie)) F[j] = f_ext, t |= 8; else F[j] = f_opn;
+            const int d = diag + mrow[c2[j - 1]];
+            int h = d, src = 0;
+            if (ins_first) {
+                if (F[j] > h) h = F[j], src = 2;
+                if (E > h) h = E, src = 1;
+            } else {
+                if (E > h) h = E, src = 1;
+                if (F[j] > h) h = F[j], src = 2;
+            }
+            T[(size_t)i * W + (size_t)j] = (uint8_t)(t | src);
+            diag = up;
+            H[j] = h;
+            left = h;
+        }
+    }
+    int best = H[0], bj = 0; /* H[n1][0] is a legal end (whole window against nothing) */
+    for (int j = 1; j <= n2; ++j)
+        if (H[j] > best || (end_last && H[j] == best)) best = H[j], bj = j;
+    if (score) *score = best;
+    if (end_ref) *end_ref = bj - 1;
+    /* traceback from (n1, bj) to row 0, then the free leading part of s2 as one 'D' run */
+    int n_ops = 0, rc = 0;
+    uint32_t *rev = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n1 + n2 + 2));
+    if (!rev) {
+        free(H), free(F), free(T), free(c2);
+        return 2;
+    }
+    {
+        int i = n1, j = bj, state = 0; /* 0 = in H, 1 = in E (horizontal run), 2 = in F (vertical run) */
+        while (i > 0) {
+            const uint8_t t = j > 0 ? T[(size_t)i * W + (size_t)j] : 2;
+            uint32_t op;
+            if (state == 0) state = t & 3;
+            if (state == 0) {
+                const int sc = matrix[STRK_NSYM * strk_oracle_symbol((unsigned char)s1[i - 1]) + c2[j - 1]];
+                op = sc > 0 ? 7u : 8u;
+                --i, --j;
+            } else if (state == 1) {
+                op = 2u; /* 'D': s2 only */
+                if (!(t & 4)) state = 0;
+                --j;
+            } else {
+                op = 1u; /* 'I': s1 only */
+                if (j == 0 || !(t & 8)) state = 0;
+                --i;
+            }
+            if (n_ops && (rev[n_ops - 1] & 15u) == op) rev[n_ops - 1] += 16u; else rev[n_ops++] = 16u | op;
+        }
+        if (j > 0) rev[n_ops++] = ((uint32_t)j << 4) | 2u; /* read bases before the window: deletions from (0, 0) */
+    }
+    if (cigar_len) *cigar_len = n_ops;
+    if (n_ops > cigar_cap || !cigar) rc = cigar ? 4 : 0;
+    else for (int k = 0; k < n_ops; ++k) cigar[k] = rev[n_ops - 1 - k];
+    free(rev), free(H), free(F), free(T), free(c2);
+    return rc;
+}

@@ -111,6 +111,16 @@ int strk_oracle_count_loci(const char *arena, const uint64_t *seq_off, const int
                            const int8_t *matrix, int flags, int tie_flags, int n_threads, int32_t *out,
                            double *cells_out);
 
+/* Soft-clip realignment, strkit/call/realign.py:56-63: parasail.sg_dx_trace_scan_16(s1 = reference window, s2 = read,
+ * open, extend, dna_matrix) -> score, end_ref (last read position aligned), CIGAR from cell (0, 0) in parasail / BAM
+ * encoding ((len << 4) | op; I = s1 only, D = s2 only, 7 '=' / 8 'X' on the diagonal).  PARITY UNPINNED (see the .c). */
+#define STRK_TRACE_OPEN_ON_TIE 1
+#define STRK_TRACE_INS_FIRST 2
+#define STRK_TRACE_END_LAST 4
+int strk_oracle_realign(const char *s1, int n1, const char *s2, int n2, int gap_open, int gap_extend,
+                        const int8_t *matrix, int trace_flags, int *score, int *end_ref, uint32_t *cigar, int cigar_cap,
+                        int *cigar_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,8 +1,11 @@
-B="python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e --sustain-s 0"
-for v in 0 1 3; do STRKIT_B200_LIB=$PWD/build/libstrk_pol$v.so $B > gpurun_out/pol$v.json 2> gpurun_out/pol$v.err; python -c "
-import json,sys
-d=json.load(open('gpurun_out/pol$v.json')); print('pol$v', d['value']/1e6, d['reads_only']['value']/1e6, d['ref_path']['ms_per_step'], d['parity_sample_bit_exact'])
-"; done
-N="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --sustain-s 0 --no-ref-path --pool 1"
-for v in 0 1 3; do STRKIT_B200_LIB=$PWD/build/libstrk_pol$v.so ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:dp_packed_kernel -c 15 --csv --log-file gpurun_out/r2_traffic_pol$v.csv $N > /dev/null 2>&1; done
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"dp_|ref_|replay|plan_|hash|dedupe|expand" -c 200 --csv --log-file gpurun_out/r2_ref_launches.csv python tools/bench_ref_path.py 32768 > gpurun_out/ncu_ref.log 2>&1; tail -2 gpurun_out/ncu_ref.log
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputests_4.log 2>&1; tail -8 gpurun_out/r2_gputests_4.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_3.json 2> gpurun_out/r2_bench_3.err; tail -3 gpurun_out/r2_bench_3.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2_bench_3.json'))
+print('value', d['value']/1e6, 'reads_only', d['reads_only']['value']/1e6, 'ref ms', d['ref_path']['ms_per_step'], 'ref dp ms', d['ref_path']['dp_kernel_ms_per_step'], 'ref frac', d['ref_path']['roofline']['frac'])
+print('e2e', d['e2e']['value']/1e6, 'e2e reads only', d['e2e']['reads_only_value']/1e6, 'blocking', d['e2e']['blocking_call_value']/1e6, 'frac', d['roofline']['frac'], 'parity', d['parity_sample'], d['ref_path']['parity_sample'])
+PY
+python bench.py --config 4 --steps 5 --warmup 2 > gpurun_out/r2_bench_cfg4.json 2> gpurun_out/r2_bench_cfg4.err; tail -c 1800 gpurun_out/r2_bench_cfg4.json; tail -3 gpurun_out/r2_bench_cfg4.err
+python bench.py --config 3 --steps 3 --warmup 2 > gpurun_out/r2_bench_cfg3.json 2> gpurun_out/r2_bench_cfg3.err; tail -c 1800 gpurun_out/r2_bench_cfg3.json; tail -3 gpurun_out/r2_bench_cfg3.err
+STRK_REF_TIMING=1 python tools/bench_ref_path.py 2>&1 | tail -4
