@@ -226,6 +226,27 @@ int strk_alleles_aggregate(strk_ctx *ctx, const double *rep_means, const double 
                            const uint8_t *rep_peaks, int64_t n_loci, int n_alleles, int num_bootstrap, int32_t *out_i,
                            double *out_d);
 
+/*
+ * Soft-clip realignment (strkit/call/realign.py:34-72): parasail.sg_dx_trace_scan_16(ref_seq, query_seq, 7, 0,
+ * dna_matrix) for n (reference window, read) pairs -- the window aligned end to end, both read ends free, affine gaps
+ * (a gap of length k costs gap_open + (k - 1) * gap_extend; the reference passes 7 and 0), traceback.
+ *   ref_off / ref_len, read_off / read_len   ASCII sequences in `arena`
+ *   score[k], end_ref[k]    parasail's result fields (end_ref = 0-based last read position aligned)
+ *   cigar + cigar_off[k]    the CIGAR from cell (0, 0) in parasail's / BAM's encoding, (len << 4) | op with I = 1 (window
+ *                           base against nothing), D = 2 (read base against nothing), '=' = 7, X = 8; the caller sizes
+ *                           each region (cigar_off has n + 1 entries) to at least 2 * ref_len + 4 entries
+ *   cigar_len[k]            entries written
+ * trace_flags: STRK_TRACE_* tie rules of the traceback that the reference tree cannot show (0 = extend on an
+ * open / extend tie, diagonal before horizontal before vertical, first best end column).  One byte of device memory
+ * per DP cell while a group of alignments is in flight (groups are cut at STRK_REALIGN_TRACE_MB, default 2048).
+ */
+#define STRK_TRACE_OPEN_ON_TIE 1
+#define STRK_TRACE_INS_FIRST 2
+#define STRK_TRACE_END_LAST 4
+int strk_realign(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *ref_off, const int32_t *ref_len,
+                 const uint64_t *read_off, const int32_t *read_len, int64_t n, int gap_open, int gap_extend, int trace_flags,
+                 int32_t *score, int32_t *end_ref, uint32_t *cigar, const uint64_t *cigar_off, int32_t *cigar_len);
+
 /* Integer issue-rate micro-benchmark: the roofline denominator of the DP kernels (MEASURED_PEAKS.json has
  * no INT32 figure).  out_tiops[0] = ALU pipe only (VIADDMNMX), [1] = FMA pipe only (IMAD), [2] = both pipes;
  * units: 1e12 lane-level 32-bit integer instructions per second, all SMs. */

@@ -63,6 +63,8 @@ def _load() -> C.CDLL:
         "strk_gmm_fit_counts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_double, C.c_int, C.c_int, _vp]),
         "strk_alleles_aggregate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]),
+        "strk_realign": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+                                   _vp]),
         "strk_get_stats": (C.c_int, [_vp, _vp]),
         "strk_measure_int_peak": (C.c_int, [_vp, _vp]),
     }
@@ -77,7 +79,7 @@ lib = _load()
 EXPORTED = ("strk_last_error", "strk_version", "strk_device_count", "strk_init", "strk_destroy", "strk_sync", "strk_host_register",
             "strk_host_unregister", "strk_batch_upload", "strk_batch_create", "strk_batch_fill", "strk_batch_fill_fmt", "strk_count_reads_fmt", "strk_batch_run", "strk_batch_download", "strk_batch_free",
             "strk_count_reads", "strk_get_repeat_count", "strk_score_tables", "strk_ref_boundary_tables", "strk_ref_counts", "strk_call_alleles", "strk_gmm_fit_counts",
-            "strk_alleles_aggregate", "strk_get_stats", "strk_measure_int_peak")
+            "strk_alleles_aggregate", "strk_realign", "strk_get_stats", "strk_measure_int_peak")
 
 
 def check(rc: int) -> None:

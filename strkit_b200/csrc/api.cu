@@ -1780,3 +1780,4 @@ extern "C" int strk_measure_int_peak(strk_ctx *ctx, double out_tiops[3]) {
 // bootstrap / GMM allele calls (the consumer of the per-read counts)
 // ------------------------------------------------------------------------------------------------
 #include "alleles_api.cuh"
+#include "realign_api.cuh"

@@ -53,6 +53,8 @@ class Oracle:
         lib.strk_oracle_count_loci.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        lib.strk_oracle_realign.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                            _i32p, _i32p, C.c_void_p, C.c_int, _i32p]
         self.matrix = np.zeros(17 * 17, dtype=np.int8)
         lib.strk_oracle_dna_matrix(self.matrix.ctypes.data)
 
@@ -76,6 +78,18 @@ class Oracle:
         if rc:
             raise ValueError(f"oracle sg_align failed: {rc}")
         return sc.value, eq.value, er.value
+
+    def realign(self, ref_seq: str, query_seq: str, gap_open: int = 7, gap_extend: int = 0, trace_flags: int = 0):
+        """parasail.sg_dx_trace_scan_16(ref_seq, query_seq, open, extend) restated: (score, end_ref, cigar uint32[])."""
+        b1, b2 = ref_seq.encode(), query_seq.encode()
+        cap = 2 * len(b1) + 4
+        cigar = np.zeros(cap, dtype=np.uint32)
+        sc, er, ln = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = self.lib.strk_oracle_realign(b1, len(b1), b2, len(b2), gap_open, gap_extend, self.matrix.ctypes.data,
+                                          trace_flags, C.byref(sc), C.byref(er), cigar.ctypes.data, cap, C.byref(ln))
+        if rc:
+            raise ValueError(f"oracle realign failed: {rc}")
+        return sc.value, er.value, cigar[:ln.value].copy()
 
     def score_candidate(self, tr: str, fl: str, fr: str, motif: str, n: int, flags: int = MODE_SG) -> int:
         db = (fl + tr + fr).encode()
