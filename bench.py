@@ -394,19 +394,39 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
             register(a)
         refs.append(ref)
     torch.cuda.empty_cache()
-    outs = [np.empty((b.n_reads, 4), dtype=np.int32) for b in mine]
-    for o in outs:
-        register(o)
     n_mine = sum(b.n_reads for b in mine)
     # read counts per rank (every rank can compute them: reads per locus is constant in this catalog)
     counts = [int((bounds[r + 1] - bounds[r]) * READS_PER_LOCUS) for r in range(world)]
     assert counts[rank] == n_mine
+    # The host-side gather (where the reference heap-merges its workers' results, call_sample.py:420): ONE result array
+    # [total reads, 4] in catalog order lives in POSIX shared memory; every rank's per-block downloads (D2H) land
+    # directly in its slice of it, so after the closing barrier rank 0 holds the whole catalog's results without
+    # another copy.  (sharding.count_reads_sharded is the torch.distributed form of the same gather, for callers
+    # without a shared address space.)
+    from multiprocessing import shared_memory
+
+    total_reads = n_blocks * block * READS_PER_LOCUS
+    shm_name = f"strk_b200_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
+    shm = None
+    if rank == 0:
+        try:
+            shared_memory.SharedMemory(name=shm_name).unlink()
+        except FileNotFoundError:
+            pass
+        shm = shared_memory.SharedMemory(name=shm_name, create=True, size=total_reads * 16)
+    barrier()
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=shm_name)
+    result = np.ndarray((total_reads, 4), dtype=np.int32, buffer=shm.buf)
+    outs, at = [], sum(counts[:rank])
+    for b_ in mine:
+        outs.append(result[at:at + b_.n_reads])
+        at += b_.n_reads
+    for o in outs:
+        register(o)
     for w in range(max(1, args.warmup)):   # warm both contexts and the recycled device buffers
         for _ in eng.count_reads_stream(mine[:2], params, outs=outs[:2], refs=refs[:2]):
             pass
-    pad = max(counts)
-    dbuf = torch.zeros((pad, 4), dtype=torch.int32, device=dev)
-    gathered = [torch.zeros_like(dbuf) for _ in range(world)] if (rank == 0 and world > 1) else None
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -416,17 +436,8 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
         pass
     torch.cuda.synchronize()
     t_compute = time.perf_counter() - t0
-    local = np.concatenate(outs) if outs else np.zeros((0, 4), dtype=np.int32)
-    if world > 1:
-        dbuf[:n_mine].copy_(torch.from_numpy(local), non_blocking=False)
-        dist.gather(dbuf, gathered, dst=0)
-        if rank == 0:
-            result = np.concatenate([g[:c].cpu().numpy() for g, c in zip(gathered, counts)], axis=0)
-    else:
-        result = local
-    torch.cuda.synchronize()
+    barrier()                                # every rank's rows are in the shared array: the gather is complete
     t_total = time.perf_counter() - t0
-    barrier()
     clocks = sampler.stop()
     t_total = reduce_max(t_total)
     per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
@@ -436,7 +447,6 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
     else:
         per_rank = [t_compute]
     if rank == 0:
-        total_reads = n_blocks * block * READS_PER_LOCUS
         assert result.shape[0] == total_reads
         # spot check of rows that came from the LAST rank's partition (and of rank 0's own) against the CPU port
         from tests import oracle_lib
@@ -466,9 +476,17 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
                         "d2h_bytes_per_step": int(sum(o.nbytes for o in outs) / max(1, len(outs)))},
                 "partition": {"loci_per_rank": [int(bounds[r + 1] - bounds[r]) for r in range(world)],
                               "compute_s_per_rank": per_rank, "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
-                              "gather_s": t_total - max(per_rank), "total_s": t_total},
+                              "gather_s": t_total - max(per_rank), "total_s": t_total,
+                              "gather": "per-block D2H straight into one shared-memory result array; closing barrier"},
                 "gpu_launches": int(eng.total_launches - launches0), "parity_sample_bit_exact": ok, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    for o in outs:
+        strkit_b200._native.lib.strk_host_unregister(o.ctypes.data)
+    del result, outs
+    barrier()
+    shm.close()
+    if rank == 0:
+        shm.unlink()
 
 
 def ref_windows_of(hb, np):

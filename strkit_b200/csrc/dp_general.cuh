@@ -116,55 +116,66 @@ __device__ __forceinline__ void gen_fast_steps(int (&H)[R], const unsigned (&sel
                                                const int *__restrict__ top, int *__restrict__ bot, const int ncols,
                                                volatile long long *prog_in, volatile long long *prog_out,
                                                const long long stride, const int b, int &pmax, const int g) {
+    // Whole chunks of 32 steps, entered with s a multiple of 32: the boundary-row refill (TOP) and the progress
+    // publication (BOT) happen between chunks, the 32 steps in between are straight-line and convergent (lane 31's
+    // boundary-row store is predicated, not branched).
     const int mbytes = m * 8;
     const char *tbase = (const char *)tM;
     int gj = g * (s - lane + 1);  // g * (column of this lane)
+    const unsigned on31 = lane == 31 ? 1u : 0u;
 #pragma unroll 1
-    for (; s < s_end; ++s) {
-        int up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
+    for (; s + 32 <= s_end; s += 32) {
         if (TOP) {
-            if ((s & 31) == 0) {
-                top_cur = top_nxt;
-                if (s + 33 <= ncols) {
-                    const long long need = (long long)(b - 1) * stride + (s + 64 < ncols ? s + 64 : ncols);
-                    while (*prog_in < need) __nanosleep(40);
-                    __threadfence_block();
-                    if (s + 33 + lane <= ncols) top_nxt = __ldcg(top + s + 33 + lane);
-                }
+            top_cur = top_nxt;
+            if (s + 33 <= ncols) {
+                const long long need = (long long)(b - 1) * stride + (s + 64 < ncols ? s + 64 : ncols);
+                while (*prog_in < need) __nanosleep(40);
+                __threadfence_block();
+                if (s + 33 + lane <= ncols) top_nxt = __ldcg(top + s + 33 + lane);
             }
-            const int t0 = __shfl_sync(0xffffffffu, top_cur, s & 31);
-            if (lane == 0) up_in = t0;
-        } else {
-            if (lane == 0) up_in = topv;
-            topv += tinc;
         }
-        const unsigned long long t = *(const unsigned long long *)(tbase + koff);
-        koff += 8;
-        koff = koff == mbytes ? 0 : koff;
-        const unsigned tlo = (unsigned)t, thi = (unsigned)(t >> 32);
-        int d = prev_up, u = up_in;
-        prev_up = up_in;
+        int *botp = BOT ? bot + (s - 30) : nullptr;  // lane 31 is at column s + k - 30 in step s + k
+#pragma unroll 2
+        for (int k = 0; k < 32; ++k) {
+            int up_in = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
+            if (TOP) {
+                const int t0 = __shfl_sync(0xffffffffu, top_cur, k);
+                up_in = lane == 0 ? t0 : up_in;
+            } else {
+                up_in = lane == 0 ? topv : up_in;
+                topv += tinc;
+            }
+            const unsigned long long t = *(const unsigned long long *)(tbase + koff);
+            koff += 8;
+            koff = koff == mbytes ? 0 : koff;
+            const unsigned tlo = (unsigned)t, thi = (unsigned)(t >> 32);
+            int d = prev_up, u = up_in;
+            prev_up = up_in;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int left = H[r];
-            const int tt = gen_add(d, (int)gen_prmt(tlo, thi, sel[r]), one);
-            const int h = max(max(tt, u), left);
-            d = left;
-            u = h;
-            H[r] = h;
+            for (int r = 0; r < R; ++r) {
+                const int left = H[r];
+                const int tt = gen_add(d, (int)gen_prmt(tlo, thi, sel[r]), one);
+                const int h = max(max(tt, u), left);
+                d = left;
+                u = h;
+                H[r] = h;
+            }
+            if (BOT)
+                asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.global.u32 [%0], %1; }" ::"l"(botp + k), "r"(H[R - 1]),
+                             "r"(on31)
+                             : "memory");
+            if (PM) {
+                pmax = max(pmax, H[R - 1] - gj);
+                gj += g;
+            }
         }
         if (BOT) {
-            if (lane == 31) {
-                const int j = s - 30;
-                bot[j] = H[R - 1];
-                if ((j & 31) == 0) {
-                    __threadfence();
-                    *prog_out = (long long)b * stride + j;
-                }
+            if (lane == 31) {  // the row is complete up to column s + 1 (lane 31's column in the chunk's last step)
+                __threadfence();
+                *prog_out = (long long)b * stride + (s + 1);
             }
+            __syncwarp();
         }
-        if (PM) pmax = max(pmax, H[R - 1] - gj);
-        gj += g;
     }
 }
 
@@ -273,8 +284,9 @@ __device__ void dp_pass_body(const PassCfg &c, const GenSmem &sc, GenSync &sy, i
         const int nsteps = c.ncols + 31;
         // steady-state range [s_a, s_b): lane 31 is past the prefix columns (s - 30 > n_pre), lane 0 has not reached the
         // first candidate column n_pre + m * n_lo (it does at step n_pre + m * n_lo - 1)
-        int s_a = c.n_pre + 31, s_b = c.n_pre + c.m * c.n_lo - 1;
+        int s_a = (c.n_pre + 31 + 31) & ~31, s_b = c.n_pre + c.m * c.n_lo - 1;  // (whole 32-step chunks from a multiple of 32)
         if (s_b > c.ncols - 1) s_b = c.ncols - 1;
+        s_b = s_a + ((s_b - s_a) & ~31);
         if (!fast_ok || s_b - s_a < 64) s_a = s_b = nsteps;  // not worth it: one general loop
         for (int s = 0; s < nsteps; ++s) {
             if (LUT && s == s_a) {
