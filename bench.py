@@ -424,8 +424,12 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
         at += b_.n_reads
     for o in outs:
         register(o)
-    for w in range(max(1, args.warmup)):   # warm both contexts and the recycled device buffers
-        for _ in eng.count_reads_stream(mine[:2], params, outs=outs[:2], refs=refs[:2]):
+    # warm both contexts and grow their recycled device buffers to the LARGEST block of the partition (a partition
+    # that starts inside a block begins with a short one: growing the buffers later would put cudaMalloc / cudaFree,
+    # which synchronise the device, inside the timed region)
+    big = max(range(len(mine)), key=lambda i: mine[i].n_reads) if mine else 0
+    for w in range(max(1, args.warmup)):
+        for _ in eng.count_reads_stream([mine[big], mine[big]], params, outs=[outs[big], outs[big]], refs=[refs[big], refs[big]]):
             pass
     sampler = ClockSampler(local_rank)
     sampler.start()

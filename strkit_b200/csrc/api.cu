@@ -275,7 +275,7 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&ctx->d_consts, sizeof(ScoreConsts)));
     CU(cudaMemcpy(ctx->d_consts, &ctx->h_consts, sizeof(ScoreConsts), cudaMemcpyHostToDevice));
-    CU(cudaMalloc((void **)&ctx->d_queue, 4 * sizeof(unsigned int)));
+    CU(cudaMalloc((void **)&ctx->d_queue, (8 + STRK_PK_NBIN + 1) * sizeof(unsigned int)));  // [8 + k]: work queue of packed class k
     CU(cudaMalloc((void **)&ctx->d_acc, 4 * sizeof(double)));
     CU(cudaMalloc((void **)&ctx->d_plan, sizeof(PlanStats)));
     CU(cudaMalloc((void **)&ctx->d_bin_off, STRK_PK_NBIN * sizeof(unsigned int)));
@@ -489,9 +489,11 @@ static int launch_packed_r(strk_ctx *ctx, const FamDesc *fams, const int *list, 
             ctx->l2_window_stream = st;
         }
     }
+    unsigned int *work_counter = ctx->d_queue + 8 + (L == 16 ? R / 2 : R);  // one queue per rows-per-lane class
+    CU(cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st));
     dp_packed_kernel<R, L><<<(unsigned)grid, pk_warps(L) * 32, smem, st>>>(fams, list, n, arena, ctx->d_consts, table, dims,
                                                                         ctx->pk_scratch.p + (scratch_off > 0 ? scratch_off : 0),
-                                                                        ctx->fallback.p, ctx->d_queue + 2, ref_mode);
+                                                                        ctx->fallback.p, ctx->d_queue + 2, ref_mode, work_counter);
     CU(cudaGetLastError());
     ctx->stats[2] += 1;
     return STRK_OK;
@@ -1506,7 +1508,11 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
         if (start_count[l] < 0 || start_count[l] > (1 << 22) || rc_params[3 * l] < 0 || rc_params[3 * l + 1] < 0 ||
             rc_params[3 * l + 2] < 0 || rc_params[3 * l + 1] > 1000 || rc_params[3 * l + 2] > 1000)
             return set_err(STRK_ERR_ARG, "strk_ref_counts: bad start count / search parameters for locus %lld", (long long)l);
-        h_wd[(size_t)l] = std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
+        // first window of the boundary search: start +- (range + 2 * step + 4), at least +- 8 sizes; a search that leaves
+        // it is redone 4x wider.  STRK_REF_WD=<n> (tuning only): +- max(n, range + step + 2) instead.
+        static const int wd_env = getenv("STRK_REF_WD") ? atoi(getenv("STRK_REF_WD")) : 0;
+        h_wd[(size_t)l] = wd_env > 0 ? std::max(wd_env, rc_params[3 * l + 1] + rc_params[3 * l + 2] + 2)
+                                     : std::max(8, rc_params[3 * l + 1] + 2 * rc_params[3 * l + 2] + 4);
         max_wd = std::max(max_wd, h_wd[(size_t)l]);
         const int n1 = lens[3 * l] + lens[3 * l + 1] + lens[3 * l + 2];
         max_n1 = std::max(max_n1, n1);

@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(pk_warps(L) * 32, PK_MIN_CTAS(R) * PK_WARPS / 
 dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list, int n_list,
                  const unsigned char *__restrict__ arena, const ScoreConsts *__restrict__ consts,
                  int *__restrict__ table, PackedDims dims, uint4 *__restrict__ scratch,
-                 int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count, int ref_mode) {
+                 int *__restrict__ fallback_list, unsigned int *__restrict__ fallback_count, int ref_mode,
+                 unsigned int *__restrict__ work_counter) {
     static_assert(R >= 2 && (L == 32 || L == 16), "rows per lane / lanes per read out of range");
     constexpr int HALVES = 32 / L;  // reads side by side in one warp
     constexpr int SK = L - 1;       // wavefront skew: lane t of a unit is t columns behind lane 0
@@ -344,10 +345,17 @@ dp_packed_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ list,
     const unsigned ginc = (unsigned)g | ((unsigned)g << 16);
     const int g2 = 2 * g;
 
-    const int n_iter = (n_list + total_units - 1) / total_units;  // the same trip count on both units of a warp
-    for (int it = 0; it < n_iter; ++it) {
+    // Work items come from a queue (one atomic per warp and read, nothing next to a 100-microsecond sweep): a launch
+    // that shares the SMs with another context's kernels (the streamed path), or whose CTAs do not all start together,
+    // no longer ends on the slowest statically assigned slice.  Both units of a warp take consecutive items.
+    (void)total_units;
+    for (;;) {
+        unsigned int base = 0u;
+        if (wlane == 0) base = atomicAdd(work_counter, (unsigned int)HALVES);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned int)n_list) break;
         // a unit without a read of its own in the last round re-runs the last read of the list and stores nothing
-        const int fam_idx_raw = unit_global + it * total_units;
+        const int fam_idx_raw = (int)base + half;
         const bool have = fam_idx_raw < n_list;
         if (!__any_sync(0xffffffffu, have)) break;
         const int fam_id = list[have ? fam_idx_raw : n_list - 1];
