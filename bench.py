@@ -377,22 +377,28 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
     bounds = sharding.partition_catalog(cost, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     # pass 2: the blocks of my partition, as host arrays (nibble-packed, pinned) + their reference windows
+    # The partition is streamed in blocks of at most `block` loci and about a twelfth of the partition: the first
+    # block's copy and the last block's download are the part of the stream that nothing overlaps, so a rank with a
+    # small partition (N = 8: 131 072 loci) takes smaller blocks.
+    sub = int(min(block, max(4096, -(-((hi - lo) // 12) // 1024) * 1024)))
     mine, refs = [], []
     for i in range(n_blocks):
         b_lo, b_hi = max(lo, i * block), min(hi, (i + 1) * block)
         if b_hi <= b_lo:
             continue
         sb_ = synth.generate(synth.CONFIGS[2], block, seed=batch_seed(0, i), device=str(dev), chunk_loci=4096)
-        ha = sb_.to_host().slice_loci(b_lo - i * block, b_hi - i * block, compact=True)
+        whole = sb_.to_host()
         del sb_
-        hb = ha.to_nibble()
-        for a in (hb.arena, hb.seq_off, hb.lens, hb.est_cn, hb.read_begin, hb.motif_off, hb.motif_len):
-            register(a)
-        mine.append(hb)
-        ref = ref_windows_of(ha, np)
-        for a in (ref[0].arena, ref[0].seq_off, ref[0].lens, ref[0].motif_off, ref[0].motif_len, ref[1], ref[2], ref[3], ref[5]):
-            register(a)
-        refs.append(ref)
+        for s0 in range(b_lo, b_hi, sub):
+            ha = whole.slice_loci(s0 - i * block, min(s0 + sub, b_hi) - i * block, compact=True)
+            hb = ha.to_nibble()
+            for a in (hb.arena, hb.seq_off, hb.lens, hb.est_cn, hb.read_begin, hb.motif_off, hb.motif_len):
+                register(a)
+            mine.append(hb)
+            ref = ref_windows_of(ha, np)
+            for a in (ref[0].arena, ref[0].seq_off, ref[0].lens, ref[0].motif_off, ref[0].motif_len, ref[1], ref[2], ref[3], ref[5]):
+                register(a)
+            refs.append(ref)
     torch.cuda.empty_cache()
     n_mine = sum(b.n_reads for b in mine)
     # read counts per rank (every rank can compute them: reads per locus is constant in this catalog)
@@ -479,6 +485,7 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
                         "h2d_bytes_per_step": int(sum(b.nbytes() for b in mine) / max(1, len(mine))),
                         "d2h_bytes_per_step": int(sum(o.nbytes for o in outs) / max(1, len(outs)))},
                 "partition": {"loci_per_rank": [int(bounds[r + 1] - bounds[r]) for r in range(world)],
+                              "loci_per_streamed_block": sub,
                               "compute_s_per_rank": per_rank, "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
                               "gather_s": t_total - max(per_rank), "total_s": t_total,
                               "gather": "per-block D2H straight into one shared-memory result array; closing barrier"},

@@ -22,8 +22,12 @@ __global__ void hash_reads_kernel(const unsigned char *__restrict__ arena, const
     const int fl = lens[3 * r], tr = lens[3 * r + 1], fr = lens[3 * r + 2];
     const int n1 = fl + tr + fr;
     const unsigned char *p = arena + seq_off[r];
+    // The hash only nominates candidates (dedupe_loci_kernel confirms them byte by byte), so it samples every third
+    // base: a third of the loads of this latency-bound kernel, and two reads that differ in one unsampled base are
+    // told apart by the confirmation instead.
     unsigned long long h = 0x9E3779B97F4A7C15ull * (unsigned long long)(lane + 1);
-    for (int i = lane; i < n1; i += 32) {
+#pragma unroll 4
+    for (int i = 3 * lane; i < n1; i += 96) {
         h ^= (unsigned long long)p[i] + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
         h *= 0x100000001B3ull;
         h ^= h >> 29;
@@ -45,6 +49,51 @@ __global__ void dedupe_loci_kernel(const unsigned char *__restrict__ arena, cons
     if (l >= n_loci) return;
     const long long r0 = read_begin[l], r1 = read_begin[l + 1];
     unsigned dups = 0;
+    if (r1 - r0 <= 32) {
+        // Up to 32 reads: lane k keeps the key of read r0 + k in registers, so the match loop runs on shuffles and
+        // votes; global memory is touched again only to confirm a candidate (and once per read for the result).
+        const int n = (int)(r1 - r0);
+        unsigned long long hk = 0ull;
+        int fl = 0, tr = 0, fr = 0, est = 0;
+        if (lane < n) {
+            const long long r = r0 + lane;
+            hk = hash[r];
+            fl = lens[3 * r], tr = lens[3 * r + 1], fr = lens[3 * r + 2], est = est_cn[r];
+        }
+        unsigned rep_mask = 0u;  // reads that are representatives so far
+        int my_rep = lane;
+        for (int k = 0; k < n; ++k) {
+            const unsigned long long h = __shfl_sync(0xffffffffu, hk, k);
+            const int kfl = __shfl_sync(0xffffffffu, fl, k), ktr = __shfl_sync(0xffffffffu, tr, k);
+            const int kfr = __shfl_sync(0xffffffffu, fr, k), kest = __shfl_sync(0xffffffffu, est, k);
+            const bool cand = lane < k && ((rep_mask >> lane) & 1u) && hk == h && fl == kfl && tr == ktr && fr == kfr && est == kest;
+            unsigned m = __ballot_sync(0xffffffffu, cand);
+            int mine = k;
+            if (m) {
+                const int n1 = kfl + ktr + kfr;
+                const unsigned char *a = arena + seq_off[r0 + k];
+                while (m && mine == k) {  // candidates in read order: the first confirmed one is the representative
+                    const int q = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned char *bq = arena + seq_off[r0 + q];
+                    unsigned diff = 0u;  // (no short circuit: the loads of a confirmation are independent and pipeline)
+#pragma unroll 4
+                    for (int i = lane; i < n1; i += 32) diff |= (unsigned)(a[i] ^ bq[i]);
+                    if (__all_sync(0xffffffffu, diff == 0u)) mine = q;
+                }
+            }
+            if (mine == k) rep_mask |= 1u << k;
+            if (lane == k) my_rep = mine;
+        }
+        if (lane < n) {
+            const long long r = r0 + lane;
+            rep[r] = (int)(r0 + my_rep);
+            if (my_rep != lane) atomicSub(&st->bin_cnt[bin[r]], 1u);
+        }
+        dups = (unsigned)(n - __popc(rep_mask));
+        if (lane == 0 && dups) atomicAdd(&st->n_dup, dups);
+        return;
+    }
     for (long long r = r0; r < r1; ++r) {
         const unsigned long long h = hash[r];
         const int fl = lens[3 * r], tr = lens[3 * r + 1], fr = lens[3 * r + 2], est = est_cn[r];
@@ -63,9 +112,10 @@ __global__ void dedupe_loci_kernel(const unsigned char *__restrict__ arena, cons
                 m &= m - 1;
                 const long long q = base + k;
                 const unsigned char *b = arena + seq_off[q];
-                bool same = true;
-                for (int i = lane; i < n1; i += 32) same = same && a[i] == b[i];
-                if (__all_sync(0xffffffffu, same)) mine = q;
+                unsigned diff = 0u;
+#pragma unroll 4
+                for (int i = lane; i < n1; i += 32) diff |= (unsigned)(a[i] ^ b[i]);
+                if (__all_sync(0xffffffffu, diff == 0u)) mine = q;
             }
         }
         if (lane == 0) {
