@@ -628,14 +628,19 @@ def main():
         rb, start, ref_size, rc, anchor, out = ref_sets[k % args.pool]
         return eng.ref_counts(rb, start, ref_size, rc, anchor)
 
+    def ref_step_async(k):   # on the GPU's second context, under the read kernels of the same block
+        rb, start, ref_size, rc, anchor, out = ref_sets[k % args.pool]
+        return eng.ref_counts_async(rb, start, ref_size, rc, anchor)
+
     # ---- integer issue-rate peak (roofline denominator), measured on this GPU now
     peak = eng.measure_int_peak()
 
     # ---- warm-up (W steps of the whole hot path)
     for w in range(args.warmup):
+        fut = ref_step_async(w) if ref_sets else None
         eng.run(dev_batches[w % args.pool], params, kernel, stream)
-        if ref_sets:
-            ref_step(w)
+        if fut:
+            fut.result()
 
     # ---- timed region 1 (headline `value`): K steps of the WHOLE hot path of a block of loci -- the once-per-locus
     # reference path (get_ref_repeat_count) + the per-read path -- read batches resident in HBM
@@ -647,15 +652,15 @@ def main():
     agg_ref = {k: 0.0 for k in STAT_KEYS}
     ev0.record()
     for k in range(args.steps):
-        if ref_sets:
-            ref_step(k)
-            st = eng.stats()
-            for key in agg_ref:
-                agg_ref[key] += st[key]
+        fut = ref_step_async(k) if ref_sets else None
         eng.run(dev_batches[k % args.pool], params, kernel, stream)
         st = eng.stats()
         for key in agg:
             agg[key] += st[key]
+        if fut:
+            st = fut.result()[1]
+            for key in agg_ref:
+                agg_ref[key] += st[key]
     ev1.record()
     barrier()
     elapsed_ms = reduce_max(ev0.elapsed_time(ev1))
@@ -668,12 +673,30 @@ def main():
     # ---- timed region 2: the read path alone (what round 1 reported as `value`), same K steps
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg2 = {k: 0.0 for k in STAT_KEYS}   # kernel times of the read path when it has the GPU to itself: the roofline's
     ev2.record()
     for k in range(args.steps):
         eng.run(dev_batches[k % args.pool], params, kernel, stream)
+        st = eng.stats()
+        for key in agg2:
+            agg2[key] += st[key]
     ev3.record()
     barrier()
     reads_only_ms = reduce_max(ev2.elapsed_time(ev3))
+
+    # ---- the reference path alone (its own kernel times and roofline: in region 1 it shares the GPU with the read kernels)
+    ref_solo = {k: 0.0 for k in STAT_KEYS}
+    ref_solo_ms = 0.0
+    if ref_sets:
+        ref_step(0)   # (this context's reference-path buffers: region 1 ran the windows on the second context)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(4):
+            ref_step(k)
+            st = eng.stats()
+            for key in ref_solo:
+                ref_solo[key] += st[key] / 4
+        ref_solo_ms = (time.perf_counter() - t0) / 4 * 1e3
 
     # ---- sustained leg: the read path over the pool for >= --sustain-s seconds, with its own clock record
     sustained = None
@@ -797,15 +820,16 @@ def main():
 
     if rank == 0:
         steps = max(1, args.steps)
-        dp_s = agg["dp_ms"] * 1e-3
-        # dominant kernel = the DP kernel of the read path; algorithmic work = 4 int32 ops per executed cell
-        achieved = agg["executed_cells"] * 4.0 / dp_s / 1e12 if dp_s > 0 else 0.0
+        dp_s = agg2["dp_ms"] * 1e-3
+        # dominant kernel = the DP kernel of the read path; algorithmic work = 4 int32 ops per executed cell; kernel
+        # time from the read-path-only region (in region 1 the kernels share the SMs with the reference windows)
+        achieved = agg2["executed_cells"] * 4.0 / dp_s / 1e12 if dp_s > 0 else 0.0
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         arena_gbs = (reads_per_step * 300.0 * args.steps) / dp_s / 1e9 if dp_s > 0 else 0.0
         traffic, traffic_src = ncu_dram_traffic()
-        n_dp_reads = agg["reads_packed_kernel"] + agg["reads_general_kernel"]
-        ref_dp_s = agg_ref["dp_ms"] * 1e-3
+        n_dp_reads = agg2["reads_packed_kernel"] + agg2["reads_general_kernel"]
+        ref_dp_s = ref_solo["dp_ms"] * 1e-3
         cfg = config_dict(args, world)
         cfg["host_affinity"] = numa_note
         line = {
@@ -813,7 +837,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32" if args.kernel == "general" else "u16x2/int32",
             "data": "synthetic", "config": cfg,
-            "value_is": "whole hot path of a block of loci: get_ref_repeat_count once per locus + get_repeat_count per read"
+            "value_is": "whole hot path of a block of loci: get_ref_repeat_count once per locus (host arrays, second native "
+                        "context, running under the read kernels) + get_repeat_count per read (batch resident in HBM)"
                         if ref_sets else "read path only (--no-ref-path)",
             "reads_only": {"value": total_reads / (reads_only_ms * 1e-3), "unit": UNIT, "ms_per_step": reads_only_ms / steps},
             "sustained": sustained,
@@ -823,8 +848,9 @@ def main():
                          "frac": achieved / peak["dual_pipe"] if peak["dual_pipe"] else None, "traffic": traffic,
                          "traffic_note": f"DRAM bytes ({traffic_src})" if traffic else None,
                          "kernel": "dp_general_kernel" if agg["reads_packed_kernel"] == 0 else "dp_packed_kernel",
-                         "ops_per_cell": 4, "kernel_ms_per_step": agg["dp_ms"] / steps,
-                         "kernel_share_of_step": agg["dp_ms"] / elapsed_ms if elapsed_ms else None,
+                         "ops_per_cell": 4, "kernel_ms_per_step": agg2["dp_ms"] / steps,
+                         "kernel_share_of_step": agg2["dp_ms"] / reads_only_ms if reads_only_ms else None,
+                         "measured_in": "the read-path-only region (reads_only)",
                          "cells_are": "executed cells of the DISTINCT reads (identical reads of a locus share one table)",
                          "distinct_reads_per_step": n_dp_reads / steps,
                          "peak_how": "measured now on this GPU: lane-level 32-bit integer instructions/s, "
@@ -833,14 +859,16 @@ def main():
                          "hbm": {"achieved": arena_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "note": "arena streaming only; the path is INT-ALU bound, not HBM bound"}},
             "ref_path": None if not ref_sets else {
-                "ms_per_step": (elapsed_ms - reads_only_ms) / steps, "loci_per_step": args.loci_per_step,
+                "ms_per_step": (elapsed_ms - reads_only_ms) / steps, "ms_per_step_is": "added to the read path's step by the "
+                "reference windows running under it (alone: tools/bench_ref_path.py)", "loci_per_step": args.loci_per_step,
                 "share_of_hot_path_time": (elapsed_ms - reads_only_ms) / elapsed_ms,
                 "share_of_executed_cells": agg_ref["executed_cells"] / max(1.0, agg["executed_cells"] + agg_ref["executed_cells"]),
-                "dp_kernel_ms_per_step": agg_ref["dp_ms"] / steps, "replay_ms_per_step": agg_ref["replay_ms"] / steps,
+                "alone_ms_per_block": ref_solo_ms, "dp_kernel_ms_per_block_alone": ref_solo["dp_ms"],
+                "replay_ms_per_block_alone": ref_solo["replay_ms"],
                 "kernel_launches_per_step": agg_ref["kernel_launches"] / steps,
-                "roofline": {"bound": "int_alu", "unit": "Tiop/s", "peak": peak["dual_pipe"],
-                             "achieved": agg_ref["executed_cells"] * 4.0 / ref_dp_s / 1e12 if ref_dp_s > 0 else None,
-                             "frac": agg_ref["executed_cells"] * 4.0 / ref_dp_s / 1e12 / peak["dual_pipe"] if ref_dp_s > 0 else None,
+                "roofline": {"bound": "int_alu", "unit": "Tiop/s", "peak": peak["dual_pipe"], "measured": "alone, 4 blocks",
+                             "achieved": ref_solo["executed_cells"] * 4.0 / ref_dp_s / 1e12 if ref_dp_s > 0 else None,
+                             "frac": ref_solo["executed_cells"] * 4.0 / ref_dp_s / 1e12 / peak["dual_pipe"] if ref_dp_s > 0 else None,
                              "kernel": "dp_packed_kernel (reference mode: both sg_qe sweeps of a locus) + the final count"},
                 "parity_sample": ref_parity,
                 "how": "Engine.ref_counts: host arrays in / 8 ints per locus out, one call per block"},

@@ -108,8 +108,7 @@ extern "C" int strk_call_alleles(strk_ctx *ctx, const int32_t *cn, const double 
         return set_err(STRK_ERR_NOMEM, "strk_call_alleles: %s", cudaGetErrorString(e));
     }
     cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    e0 = ctx->ev[0], e1 = ctx->ev[1];  // context-owned: nothing to release on an error path
     CU(cudaEventRecord(e0, st));
     CU(cudaMemsetAsync(d_kmax, 0, sizeof(int), st));
     alleles_prepare_kernel<<<(unsigned)((n_loci + 127) / 128), 128, 0, st>>>(d_cn, d_w, d_rb, (int)n_loci, min_reads, kcap,
@@ -165,8 +164,6 @@ extern "C" int strk_call_alleles(strk_ctx *ctx, const int32_t *cn, const double 
         CU(cudaEventElapsedTime(&ms, e0, e1));
         *ms_out = (double)ms;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return STRK_OK;
 }
 

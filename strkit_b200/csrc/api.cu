@@ -89,6 +89,12 @@ struct strk_ctx {
     cudaEvent_t side_ev[STRK_PK_NBIN] = {nullptr};
     cudaEvent_t fork_ev = nullptr;
     cudaStream_t stream = nullptr;
+    // Uploads and planning kernels of strk_batch_fill run on a LOW-priority stream, the DP streams are created with the
+    // greatest priority: in the streamed path the fill of block i + 1 (two contexts) shares the GPU with the DP kernels
+    // of block i, and its large grids of short blocks (one warp per read) would otherwise take the slots every
+    // finishing DP class frees before the next class' CTAs can.
+    cudaStream_t fill_stream = nullptr;
+    int prio_hi = 0;
     ScoreConsts h_consts;
     ScoreConsts *d_consts = nullptr;
     int gap = 5, end_flags = STRK_MODE_SG, tie_flags = 0;
@@ -107,6 +113,8 @@ struct strk_ctx {
     DevBuf<unsigned long long> ref_u64[2];
     DevBuf<int> ref_i[13];
     struct strk_batch *ref_batch = nullptr;
+    std::vector<int> ref_flat, ref_hwd;  // host sources of asynchronous copies of the reference path's fast path
+    DevBuf<int> ref_out;                 // its results, assembled on the device
     DevBuf<int> al_i[8];             //                 per-read / per-locus integer arrays (recycled across calls)
     DevBuf<double> al_d[3];
     DevBuf<long long> al_rb;
@@ -114,7 +122,7 @@ struct strk_ctx {
     double *d_acc = nullptr;          // [0] ref cells, [1] executed cells
     PlanStats *d_plan = nullptr;      // device-side planning counters
     unsigned int *d_bin_off = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     struct strk_batch *reuse = nullptr;  // device buffers recycled by strk_count_reads
 };
@@ -170,6 +178,8 @@ static void build_lut(unsigned char lut[256]) {
     }
 }
 
+extern "C" int strk_destroy(strk_ctx *ctx);
+
 extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM], int gap_open, int gap_extend,
                          int end_flags, int tie_flags, strk_ctx **out) {
     if (!out || !matrix) return set_err(STRK_ERR_ARG, "strk_init: null argument");
@@ -197,6 +207,13 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     }
     strk_ctx *ctx = new (std::nothrow) strk_ctx();
     if (!ctx) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    // any failure below releases what has been created so far (strk_destroy copes with a half-built context)
+    struct Guard {
+        strk_ctx *c;
+        ~Guard() {
+            if (c) strk_destroy(c);
+        }
+    } guard{ctx};
     ctx->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -217,10 +234,7 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     for (int a = 0; a < STRK_NSYM; ++a)
         for (int b = 0; b < STRK_NSYM; ++b) {
             int v = matrix[a * STRK_NSYM + b];
-            if (v < -60 || v > 60) {
-                delete ctx;
-                return set_err(STRK_ERR_ARG, "matrix entry %d out of range [-60, 60]", v);
-            }
+            if (v < -60 || v > 60) return set_err(STRK_ERR_ARG, "matrix entry %d out of range [-60, 60]", v);
             ctx->h_consts.smat[a * STRK_NSYM + b] = (signed char)v;
         }
     for (int b = 0; b < STRK_NSYM; ++b) {
@@ -272,14 +286,21 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
         ctx->h_consts.one_table_ok = one;
         for (int k = 0; k < 32; ++k) ctx->h_consts.one_v[k] = 1u;
     }
-    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least, hi = greatest (numerically smaller)
+        ctx->prio_hi = hi;
+        CU(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&ctx->fill_stream, cudaStreamNonBlocking, lo));
+    }
     CU(cudaMalloc((void **)&ctx->d_consts, sizeof(ScoreConsts)));
     CU(cudaMemcpy(ctx->d_consts, &ctx->h_consts, sizeof(ScoreConsts), cudaMemcpyHostToDevice));
     CU(cudaMalloc((void **)&ctx->d_queue, (8 + STRK_PK_NBIN + 1) * sizeof(unsigned int)));  // [8 + k]: work queue of packed class k
     CU(cudaMalloc((void **)&ctx->d_acc, 4 * sizeof(double)));
     CU(cudaMalloc((void **)&ctx->d_plan, sizeof(PlanStats)));
     CU(cudaMalloc((void **)&ctx->d_bin_off, STRK_PK_NBIN * sizeof(unsigned int)));
-    for (int k = 0; k < 3; ++k) CU(cudaEventCreate(&ctx->ev[k]));
+    for (int k = 0; k < 6; ++k) CU(cudaEventCreate(&ctx->ev[k]));
+    guard.c = nullptr;
     *out = ctx;
     return STRK_OK;
 }
@@ -291,6 +312,7 @@ extern "C" int strk_sync(strk_ctx *ctx) {
     CU(cudaSetDevice(ctx->device));
     for (int k = 0; k < STRK_PK_NBIN; ++k)
         if (ctx->side[k]) CU(cudaStreamSynchronize(ctx->side[k]));
+    CU(cudaStreamSynchronize(ctx->fill_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return STRK_OK;
 }
@@ -304,6 +326,7 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     if (ctx->ref_batch) strk_batch_free(ctx, ctx->ref_batch);
     ctx->ref_batch = nullptr;
     ctx->ref_arena.release();
+    ctx->ref_out.release();
     for (int k = 0; k < 2; ++k) ctx->ref_u64[k].release();
     for (int k = 0; k < 13; ++k) ctx->ref_i[k].release();
     ctx->scratch.release();
@@ -326,13 +349,14 @@ extern "C" int strk_destroy(strk_ctx *ctx) {
     if (ctx->d_acc) cudaFree(ctx->d_acc);
     if (ctx->d_plan) cudaFree(ctx->d_plan);
     if (ctx->d_bin_off) cudaFree(ctx->d_bin_off);
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 6; ++k)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < STRK_PK_NBIN; ++k) {
         if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
         if (ctx->side_ev[k]) cudaEventDestroy(ctx->side_ev[k]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->fill_stream) cudaStreamDestroy(ctx->fill_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return STRK_OK;
@@ -366,7 +390,7 @@ static int validate_reads(const char *who, uint64_t arena_bytes, const uint64_t 
         const int64_t n1 = (int64_t)a + b + c;
         if (n1 <= 0) return set_err(STRK_ERR_ARG, "%s: read %lld is empty (fl + tr + fr has no bases)", who, (long long)r);
         if (n1 > (1 << 24)) return set_err(STRK_ERR_ARG, "%s: read %lld is too long (%lld)", who, (long long)r, (long long)n1);
-        if (seq_off[r] + (uint64_t)n1 > arena_bytes)
+        if (seq_off[r] > arena_bytes || (uint64_t)n1 > arena_bytes - seq_off[r])
             return set_err(STRK_ERR_ARG, "%s: read %lld runs past the end of the arena", who, (long long)r);
     }
     return STRK_OK;
@@ -376,7 +400,7 @@ static int validate_motifs(const char *who, uint64_t arena_bytes, const uint64_t
                            int64_t n) {
     for (int64_t l = 0; l < n; ++l) {
         if (motif_len[l] <= 0) return set_err(STRK_ERR_ARG, "%s: motif %lld is empty", who, (long long)l);
-        if (motif_off[l] + (uint64_t)motif_len[l] > arena_bytes)
+        if (motif_off[l] > arena_bytes || (uint64_t)motif_len[l] > arena_bytes - motif_off[l])
             return set_err(STRK_ERR_ARG, "%s: motif %lld runs past the end of the arena", who, (long long)l);
     }
     return STRK_OK;
@@ -594,7 +618,7 @@ static int launch_packed_classes(strk_ctx *ctx, const int *const *list, const lo
         if (!cnt[k]) continue;
         const PackedDims dims = pk_dims_for_class(k, flank[k], mmax[k], w_max[k]);
         if (fan_out && fan_off[k] >= 0) {
-            if (!ctx->side[k]) CU(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+            if (!ctx->side[k]) CU(cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, ctx->prio_hi));
             if (!ctx->side_ev[k]) CU(cudaEventCreateWithFlags(&ctx->side_ev[k], cudaEventDisableTiming));
             CU(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev, 0));
             rc = launch_packed(ctx, k, fams, list[k], (int)cnt[k], arena, (int *)table, dims, ctx->side[k], ref_mode, nullptr,
@@ -647,7 +671,7 @@ static int launch_pass(strk_ctx *ctx, const int *const *list, const long long *c
     }
     int rc = STRK_OK;
     if (overlap) {
-        if (!ctx->side[0]) CU(cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking));
+        if (!ctx->side[0]) CU(cudaStreamCreateWithPriority(&ctx->side[0], cudaStreamNonBlocking, ctx->prio_hi));
         if (!ctx->side_ev[0]) CU(cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
         if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ctx->fork_ev, st));
@@ -696,7 +720,7 @@ extern "C" int strk_batch_free(strk_ctx *ctx, strk_batch *b) {
 // Validation + work planning of a batch whose arrays are already on the device (b->d_*, n_reads, n_loci set).
 static int batch_plan(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes) {
     const long long n_reads = b->n_reads, n_loci = b->n_loci;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->fill_stream;  // (callers hand over host-synchronised data; every path below ends synchronised)
     b->d_rep = nullptr;
     b->n_dup = 0;
     if (n_reads == 0) {
@@ -780,7 +804,7 @@ static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, c
                            const int32_t *est_cn, const int64_t *read_begin, const uint64_t *motif_off,
                            const int32_t *motif_len) {
     const long long n_reads = b->n_reads, n_loci = b->n_loci;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->fill_stream;
     b->d_rep = nullptr;  // small batches: every read gets its own table
     b->n_dup = 0;
     if (n_reads == 0) {
@@ -805,7 +829,7 @@ static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, c
         }
         if (motif_len[l] <= 0)
             report(l, PLAN_ERR_MOTIF_EMPTY);
-        else if (motif_off[l] + (unsigned long long)motif_len[l] > arena_bytes)
+        else if (motif_off[l] > arena_bytes || (unsigned long long)motif_len[l] > arena_bytes - motif_off[l])
             report(l, PLAN_ERR_MOTIF_PAST_ARENA);
         for (long long r = r0; r < r1; ++r) read_locus[(size_t)r] = (int)l;
     }
@@ -822,9 +846,10 @@ static int batch_plan_host(strk_ctx *ctx, strk_batch *b, uint64_t arena_bytes, c
                 report(r, PLAN_ERR_EMPTY);
             else if (n1 > (1 << 24))
                 report(r, PLAN_ERR_TOO_LONG);
-            else if (seq_off[r] + (unsigned long long)n1 > arena_bytes)
+            else if (seq_off[r] > arena_bytes || (unsigned long long)n1 > arena_bytes - seq_off[r])
                 report(r, PLAN_ERR_PAST_ARENA);
-            else if (est < 0 || est > (1 << 22))
+            else if (est < 0 || est > (1 << 22) ||
+                     (long long)motif_len[read_locus[(size_t)r]] * (long long)est > (1ll << 24))
                 report(r, PLAN_ERR_EST);
             else {
                 const int m = motif_len[read_locus[(size_t)r]];
@@ -893,7 +918,7 @@ static int batch_fill(strk_ctx *ctx, strk_batch *b, const uint8_t *arena, uint64
     for (int k = 0; k < STRK_PK_NBIN; ++k) b->bin_off[k] = b->bin_cnt[k] = 0, b->bin_mmax[k] = b->bin_flank[k] = 0;
     b->max_n1 = b->mb_cols_base = b->mb_m = 0;
 
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->fill_stream;
     cudaError_t e = cudaSuccess;
 #define UP(buf, dst, src, n) \
     if (e == cudaSuccess) e = upload(b->buf, &b->dst, src, (size_t)(n), st)
@@ -1490,12 +1515,67 @@ static int dp_tables_to_host(strk_ctx *ctx, bool ref, const std::vector<FamDesc>
 // + the dual-score search replayed one thread per locus -> l_offset / r_offset; loci whose search leaves the
 // window are redone 4x wider.  Phase 2: the final get_repeat_count on the adjusted flanks = the read-path batch
 // machinery (packed kernel, device replay, widening) with one "read" per locus, one run per search-parameter tier.
+static int ref_counts_fast(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                           const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
+                           const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off, const int32_t *motif_len,
+                           int vcf_anchor_size, int32_t *out, std::vector<int> &redo, bool *taken);
+static int ref_counts_slow(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                           const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
+                           const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off,
+                           const int32_t *motif_len, int vcf_anchor_size, int respect_coords, int32_t *out);
+
+// Fast path first (one host synchronisation for the whole call: every decision between the kernels is taken on the
+// device); the loci it could not finish -- a search that left its first window -- and the calls it does not take
+// (several search-parameter tiers, respect_coords) go through the general path below, pass by pass.
 extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
                                const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
                                const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off,
                                const int32_t *motif_len, int vcf_anchor_size, int respect_coords, int32_t *out) {
     if (!ctx || !arena || !seq_off || !lens || !start_count || !ref_size || !rc_params || !motif_off || !motif_len || !out)
         return set_err(STRK_ERR_ARG, "strk_ref_counts: null argument");
+    if (n_loci <= 0 || n_loci > 0x7ffffff0LL) return set_err(STRK_ERR_ARG, "strk_ref_counts: bad locus count");
+    static const bool no_fast = getenv("STRK_REF_SLOW") != nullptr;  // (measurement only)
+    bool taken = false;
+    std::vector<int> redo;
+    if (!respect_coords && !no_fast) {
+        int rc = ref_counts_fast(ctx, arena, arena_bytes, seq_off, lens, start_count, ref_size, rc_params, n_loci, motif_off,
+                                 motif_len, vcf_anchor_size, out, redo, &taken);
+        if (rc) return rc;
+    }
+    if (!taken)
+        return ref_counts_slow(ctx, arena, arena_bytes, seq_off, lens, start_count, ref_size, rc_params, n_loci, motif_off,
+                               motif_len, vcf_anchor_size, respect_coords, out);
+    if (redo.empty()) return STRK_OK;
+    // the few loci left over: their own little call through the general path (compact copies of their sequences)
+    double keep[8];
+    memcpy(keep, ctx->stats, sizeof(keep));
+    const size_t nr = redo.size();
+    std::vector<unsigned char> sub_arena;
+    std::vector<uint64_t> so(nr), mo(nr);
+    std::vector<int32_t> ln(3 * nr), sc(nr), rs(nr), rcp(3 * nr), ml(nr), sub_out(8 * nr);
+    for (size_t q = 0; q < nr; ++q) {
+        const int l = redo[q];
+        const int n1 = lens[3 * l] + lens[3 * l + 1] + lens[3 * l + 2];
+        so[q] = sub_arena.size();
+        sub_arena.insert(sub_arena.end(), arena + seq_off[l], arena + seq_off[l] + n1);
+        mo[q] = sub_arena.size();
+        sub_arena.insert(sub_arena.end(), arena + motif_off[l], arena + motif_off[l] + motif_len[l]);
+        for (int k = 0; k < 3; ++k) ln[3 * q + k] = lens[3 * l + k], rcp[3 * q + k] = rc_params[3 * l + k];
+        sc[q] = start_count[l], rs[q] = ref_size[l], ml[q] = motif_len[l];
+    }
+    int rc = ref_counts_slow(ctx, sub_arena.data(), sub_arena.size(), so.data(), ln.data(), sc.data(), rs.data(), rcp.data(),
+                             (int64_t)nr, mo.data(), ml.data(), vcf_anchor_size, 0, sub_out.data());
+    if (rc) return rc;
+    for (size_t q = 0; q < nr; ++q) memcpy(out + 8 * (size_t)redo[q], sub_out.data() + 8 * q, 8 * sizeof(int32_t));
+    for (int k = 0; k < 8; ++k) ctx->stats[k] += keep[k];
+    ctx->stats[5] = keep[5] + (double)nr;  // loci redone
+    return STRK_OK;
+}
+
+static int ref_counts_slow(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                           const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
+                           const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off,
+                           const int32_t *motif_len, int vcf_anchor_size, int respect_coords, int32_t *out) {
     if (n_loci <= 0 || n_loci > 0x7ffffff0LL) return set_err(STRK_ERR_ARG, "strk_ref_counts: bad locus count");
     int rc = validate_reads("strk_ref_counts", arena_bytes, seq_off, lens, n_loci);
     if (rc) return rc;
@@ -1505,7 +1585,8 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
     std::vector<int> h_wd((size_t)n_loci);
     int max_wd = 6, max_n1 = 0, mb_cols = 0, mb_m = 0;
     for (int64_t l = 0; l < n_loci; ++l) {
-        if (start_count[l] < 0 || start_count[l] > (1 << 22) || rc_params[3 * l] < 0 || rc_params[3 * l + 1] < 0 ||
+        if (start_count[l] < 0 || start_count[l] > (1 << 22) ||
+            (long long)motif_len[l] * (long long)start_count[l] > (1ll << 24) || rc_params[3 * l] < 0 || rc_params[3 * l + 1] < 0 ||
             rc_params[3 * l + 2] < 0 || rc_params[3 * l + 1] > 1000 || rc_params[3 * l + 2] > 1000)
             return set_err(STRK_ERR_ARG, "strk_ref_counts: bad start count / search parameters for locus %lld", (long long)l);
         // first window of the boundary search: start +- max(6, range + step + 2) sizes, like the read path's (a search
@@ -1748,19 +1829,244 @@ extern "C" int strk_ref_counts(strk_ctx *ctx, const uint8_t *arena, uint64_t are
     return STRK_OK;
 }
 
+// The fast path of strk_ref_counts: one search-parameter tier, first windows that fit the packed kernel.  Everything
+// from the upload to the assembled results is queued on the context's stream without a host round trip in between:
+// phase 1 (boundary tables + dual-score replay), phase 2 (the final count: the same loci as one "read" each through
+// the read-path kernels -- their rows-per-lane class depends on the window's length only, which moving bases between
+// flank and tract does not change, so the class lists built on the host for phase 1 serve both phases and no device-side
+// planning pass is needed), and a kernel that assembles the 8 result ints per locus.  ONE synchronisation at the end
+// brings back the results and the flags of the loci whose search left a window; those are returned in `redo`.
+// (The general path takes 8 host synchronisations per call: harmless alone, but under another context's read kernels
+// every one of them waits for SM slots that the persistent read CTAs free only at the end of a class launch.)
+static int ref_counts_fast(strk_ctx *ctx, const uint8_t *arena, uint64_t arena_bytes, const uint64_t *seq_off,
+                           const int32_t *lens, const int32_t *start_count, const int32_t *ref_size,
+                           const int32_t *rc_params, int64_t n_loci, const uint64_t *motif_off, const int32_t *motif_len,
+                           int vcf_anchor_size, int32_t *out, std::vector<int> &redo, bool *taken) {
+    *taken = false;
+    if (!ctx->h_consts.packed_ok) return STRK_OK;
+    for (int64_t l = 1; l < n_loci; ++l)
+        if (rc_params[3 * l] != rc_params[0] || rc_params[3 * l + 1] != rc_params[1] || rc_params[3 * l + 2] != rc_params[2])
+            return STRK_OK;  // several tiers: the general path groups them
+    const int max_iters = rc_params[0], range = rc_params[1], step = rc_params[2];
+    int rc = validate_reads("strk_ref_counts", arena_bytes, seq_off, lens, n_loci);
+    if (rc) return rc;
+    rc = validate_motifs("strk_ref_counts", arena_bytes, motif_off, motif_len, n_loci);
+    if (rc) return rc;
+    if (max_iters < 0 || range < 0 || step < 0 || range > 1000 || step > 1000)
+        return set_err(STRK_ERR_ARG, "strk_ref_counts: bad search parameters");
+    static const int wd_env = getenv("STRK_REF_WD") ? atoi(getenv("STRK_REF_WD")) : 6;
+    const int wd1 = std::max(wd_env > 0 ? wd_env : 6, range + step + 2);
+    const int stride_w = 2 * wd1 + 1;
+    int wd2 = range + step + 2;  // phase 2: the read path's first window
+    if (wd2 < 6) wd2 = 6;
+    const int W2 = 2 * wd2 + 1;
+    if (2 * stride_w > PK_WINDOW_MAX || W2 > PK_WINDOW_MAX) return STRK_OK;
+    const size_t n = (size_t)n_loci;
+    int max_n1 = 0, mb_cols = 0, mb_m = 0;
+    std::vector<int> lists[STRK_PK_NBIN];
+    int mmax[STRK_PK_NBIN] = {0}, flank[STRK_PK_NBIN] = {0};
+    double cells1 = 0.0;
+    for (int64_t l = 0; l < n_loci; ++l) {
+        if (start_count[l] < 0 || start_count[l] > (1 << 22) || (long long)motif_len[l] * (long long)start_count[l] > (1ll << 24))
+            return set_err(STRK_ERR_ARG, "strk_ref_counts: bad start count / search parameters for locus %lld", (long long)l);
+        const int fl = lens[3 * l], tr = lens[3 * l + 1], fr = lens[3 * l + 2], m = motif_len[l];
+        const int n1 = fl + tr + fr;
+        max_n1 = std::max(max_n1, n1);
+        if (n1 > 32 * 16) {
+            // boundary row of multi-strip sweeps: the longest candidate prefix of either phase (phase 2 moves at most
+            // both flanks into the tract: (fl + fr) / m + 1 more copies)
+            mb_cols = std::max(mb_cols, std::max(fl, fr) + m * (start_count[l] + (fl + fr) / m + 1));
+            mb_m = std::max(mb_m, m);
+        }
+        int R = strk_pick_rows_packed(n1 + 1);
+        if (fl < 1 || fr < 1 || fl > PK_FLANK_MAX || fr > PK_FLANK_MAX || m * R > 128) R = 0;
+        lists[R].push_back((int)l);
+        mmax[R] = std::max(mmax[R], m);
+        flank[R] = std::max(flank[R], std::max(fl, fr));
+        cells1 += (double)n1 * ((double)fl + fr + 2.0 * m * ((double)start_count[l] + wd1));
+    }
+    *taken = true;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int k = 0; k < 8; ++k) ctx->stats[k] = 0;
+    // ---- device buffers (context-owned, recycled)
+    cudaError_t e = ctx->ref_arena.reserve((size_t)arena_bytes);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = ctx->ref_u64[k].reserve(n);
+    const size_t isz[13] = {3 * n, n, n, 3 * n, n, n, n, n, n, n, n, 8, n};
+    for (int k = 0; k < 13 && e == cudaSuccess; ++k) e = ctx->ref_i[k].reserve(isz[k]);
+    if (e == cudaSuccess) e = ctx->ref_out.reserve(8 * n + 8);
+    if (!ctx->ref_batch) ctx->ref_batch = new (std::nothrow) strk_batch();
+    if (!ctx->ref_batch) return set_err(STRK_ERR_NOMEM, "out of host memory");
+    strk_batch *b = ctx->ref_batch;
+    if (e == cudaSuccess) e = b->seq_off.reserve(n);
+    if (e == cudaSuccess) e = b->lens.reserve(3 * n);
+    if (e == cudaSuccess) e = b->est.reserve(n);
+    if (e == cudaSuccess) e = b->motif_off.reserve(n);
+    if (e == cudaSuccess) e = b->motif_len.reserve(n);
+    if (e == cudaSuccess) e = b->read_begin.reserve(n + 1);
+    if (e == cudaSuccess) e = b->read_locus.reserve(n);
+    if (e == cudaSuccess) e = b->out.reserve(4 * n);
+    if (e == cudaSuccess) e = b->status.reserve(n);
+    // second look at phase 1, still on the device: up to CAP2 loci whose search left the first window, 4x wider
+    const int CAP2 = 4096;
+    const int WD_MAX = (STRK_MAX_WINDOW - 1) / 2;
+    const int wd1b = std::min(WD_MAX, 4 * wd1), stride_w2 = 2 * wd1b + 1;
+    if (e == cudaSuccess) e = ctx->fams.reserve(std::max(n, (size_t)CAP2));
+    if (e == cudaSuccess) e = ctx->table64.reserve(std::max(n * (size_t)stride_w * 2, (size_t)CAP2 * (size_t)stride_w2 * 2));
+    if (e == cudaSuccess) e = ctx->table.reserve(n * (size_t)W2);
+    if (e == cudaSuccess) e = ctx->fallback.reserve(n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "strk_ref_counts: %s", cudaGetErrorString(e));
+    }
+    unsigned char *d_arena = ctx->ref_arena.p;
+    unsigned long long *d_seq_off = ctx->ref_u64[0].p, *d_motif_off = ctx->ref_u64[1].p;
+    int *d_lens = ctx->ref_i[0].p, *d_start = ctx->ref_i[1].p, *d_ref_size = ctx->ref_i[2].p, *d_rc = ctx->ref_i[3].p;
+    int *d_motif_len = ctx->ref_i[4].p, *d_wd = ctx->ref_i[5].p, *d_l_off = ctx->ref_i[6].p, *d_r_off = ctx->ref_i[7].p;
+    int *d_n_off = ctx->ref_i[8].p, *d_again = ctx->ref_i[9].p, *d_lists = ctx->ref_i[12].p;
+    unsigned int *d_cnt = (unsigned int *)ctx->ref_i[11].p;
+    ctx->ref_hwd.assign(n, wd1);
+    ctx->ref_flat.clear();
+    size_t at[STRK_PK_NBIN];
+    for (int k = 0; k < STRK_PK_NBIN; ++k) {
+        at[k] = ctx->ref_flat.size();
+        ctx->ref_flat.insert(ctx->ref_flat.end(), lists[k].begin(), lists[k].end());
+    }
+    CU(cudaMemcpyAsync(d_arena, arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_seq_off, seq_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_motif_off, motif_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_lens, lens, 3 * n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_start, start_count, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ref_size, ref_size, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rc, rc_params, 3 * n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_motif_len, motif_len, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_wd, ctx->ref_hwd.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_lists, ctx->ref_flat.data(), ctx->ref_flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_l_off, 0, n * sizeof(int), st));
+    CU(cudaMemsetAsync(d_r_off, 0, n * sizeof(int), st));
+    CU(cudaMemsetAsync(d_n_off, 0, n * sizeof(int), st));
+    CU(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctx->d_acc, 0, 4 * sizeof(double), st));
+    CU(cudaMemsetAsync(ctx->d_queue + 1, 0, 3 * sizeof(unsigned int), st));
+    const int T = 128;
+    const int b_len = max_n1 + 2;
+    const int rowlen = max_n1 > 32 * 16 ? mb_cols + mb_m * std::max(std::max(wd1, wd2), wd1b) + 2 : 2;
+    const int *seg_list[STRK_PK_NBIN];
+    long long seg_cnt[STRK_PK_NBIN];
+    int seg_w1[STRK_PK_NBIN], seg_w2[STRK_PK_NBIN];
+    for (int k = 0; k < STRK_PK_NBIN; ++k) {
+        seg_list[k] = d_lists + at[k];
+        seg_cnt[k] = (long long)lists[k].size();
+        seg_w1[k] = 2 * stride_w - 1;
+        seg_w2[k] = (W2 + 3) / 4 * 4;
+    }
+    // ---- phase 1
+    ref_plan1_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(nullptr, (int)n, d_seq_off, d_lens, d_start, d_wd, d_motif_off,
+                                                               d_motif_len, stride_w, ctx->fams.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[0], st));
+    long long n_packed = 0;
+    rc = launch_pass(ctx, seg_list, seg_cnt, flank, mmax, seg_w1, n_loci, ctx->fams.p, d_arena, ctx->table64.p, b_len, rowlen, st,
+                     1, &n_packed);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[1], st));
+    ref_replay1_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(nullptr, (int)n, ctx->table64.p, ctx->fams.p, d_start, d_rc,
+                                                                 d_ref_size, vcf_anchor_size, WD_MAX, d_wd, d_l_off, d_r_off,
+                                                                 d_n_off, d_again, d_cnt);
+    CU(cudaGetLastError());
+    {
+        // the loci whose search left the first window (a percent of a block at +-6 sizes): 4x wider through the general
+        // kernel, list and count on the device (d_again, d_cnt[0]); what still does not settle is left to the host
+        int *d_again2 = ctx->ref_i[10].p;
+        ref_clamp_count_kernel<<<1, 32, 0, st>>>(d_cnt, (unsigned)CAP2);  // (loci beyond the cap keep their flag: host redo)
+        ref_plan1_kernel<<<(unsigned)((CAP2 + T - 1) / T), T, 0, st>>>(d_again, CAP2, d_seq_off, d_lens, d_start, d_wd, d_motif_off,
+                                                                      d_motif_len, stride_w2, ctx->fams.p, d_cnt);
+        CU(cudaGetLastError());
+        rc = launch_general(ctx, true, ctx->fams.p, nullptr, CAP2, d_arena, ctx->table64.p, b_len, rowlen, st, d_cnt);
+        if (rc) return rc;
+        ref_replay1_kernel<<<(unsigned)((CAP2 + T - 1) / T), T, 0, st>>>(d_again, CAP2, ctx->table64.p, ctx->fams.p, d_start, d_rc,
+                                                                        d_ref_size, vcf_anchor_size, WD_MAX, d_wd, d_l_off,
+                                                                        d_r_off, d_n_off, d_again2, d_cnt + 4, d_cnt);
+        CU(cudaGetLastError());
+    }
+    // ---- phase 2 (loci whose phase 1 is not final yet run with their unadjusted flanks; their rows are redone)
+    b->n_reads = b->n_loci = (long long)n;
+    b->d_arena = d_arena;
+    b->d_seq_off = b->seq_off.p, b->d_lens = b->lens.p, b->d_est = b->est.p, b->d_motif_off = b->motif_off.p;
+    b->d_motif_len = b->motif_len.p, b->d_read_begin = b->read_begin.p, b->d_read_locus = b->read_locus.p;
+    b->d_out = b->out.p, b->d_status = b->status.p;
+    ref_plan2_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(nullptr, (int)n, d_seq_off, d_lens, d_start, d_motif_off,
+                                                               d_motif_len, d_l_off, d_r_off, b->d_seq_off, b->d_lens, b->d_est,
+                                                               b->d_motif_off, b->d_motif_len, b->d_read_begin, b->d_read_locus);
+    CU(cudaGetLastError());
+    plan_reads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nullptr, (long long)n, b->d_seq_off, b->d_lens, b->d_est,
+                                                                  b->d_read_locus, b->d_motif_off, b->d_motif_len, wd2, 0, W2,
+                                                                  ctx->fams.p, ctx->d_acc + 1, nullptr);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[2], st));
+    CU(cudaMemsetAsync(ctx->d_queue + 2, 0, sizeof(unsigned int), st));
+    long long n_packed2 = 0;
+    rc = launch_pass(ctx, seg_list, seg_cnt, flank, mmax, seg_w2, n_loci, ctx->fams.p, d_arena, ctx->table.p, b_len, rowlen, st, 0,
+                     &n_packed2);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[3], st));
+    if (W2 <= REPLAY_WMAX)
+        replay_reads_small_kernel<<<(unsigned)((n + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, 0, st>>>(
+            ctx->table.p, W2, wd2, 0, nullptr, nullptr, (int)n, b->d_read_begin, b->d_est, b->d_lens, b->d_motif_len, max_iters,
+            range, step, ctx->tie_flags, b->d_out, b->d_status, ctx->d_queue + 1, ctx->d_acc, nullptr);
+    else
+        replay_reads_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
+            ctx->table.p, W2, wd2, 0, nullptr, nullptr, (int)n, b->d_read_begin, b->d_est, b->d_lens, b->d_motif_len, max_iters,
+            range, step, ctx->tie_flags, b->d_out, b->d_status, ctx->d_queue + 1, ctx->d_acc, nullptr);
+    CU(cudaGetLastError());
+    ref_assemble_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>((int)n, b->d_out, b->d_status, d_lens, d_l_off, d_r_off, d_n_off,
+                                                                  ctx->ref_out.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[4], st));
+    // ---- the one synchronisation: results, flags, counters
+    std::vector<unsigned char> status(n);
+    unsigned int h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double acc[2] = {0, 0};
+    CU(cudaMemcpyAsync(out, ctx->ref_out.p, 8 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status.data(), b->d_status, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(acc, ctx->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_cnt[1] || h_cnt[5]) {
+        const long long l = (long long)(0x7fffffffu - (h_cnt[1] ? h_cnt[1] : h_cnt[5]));
+        return set_err(STRK_ERR_SEARCH, "strk_ref_counts: locus %lld scored no size (max_iters = %d)", l, max_iters);
+    }
+    // loci to redo through the general path: phase 1 left its window (flagged in the assembled row), or phase 2 did
+    for (size_t l = 0; l < n; ++l)
+        if (status[l] || out[8 * l + 4] < 0) redo.push_back((int)l);
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+    CU(cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(&t2, ctx->ev[1], ctx->ev[2]));
+    CU(cudaEventElapsedTime(&t3, ctx->ev[2], ctx->ev[3]));
+    CU(cudaEventElapsedTime(&t4, ctx->ev[3], ctx->ev[4]));
+    ctx->stats[0] = cells1 + acc[1];
+    ctx->stats[1] = acc[0];
+    ctx->stats[2] += 7;  // (launch_* count their own)
+    ctx->stats[3] = t1 + t3;
+    ctx->stats[4] = t2 + t4;
+    ctx->stats[5] = 0;
+    if (getenv("STRK_REF_TIMING"))
+        fprintf(stderr, "[strk_ref_counts] fast path, %lld loci: DP kernels %.2f + %.2f ms, replay / second look / planning kernels "
+                "%.2f + %.2f ms (device clock), %u loci took the second look, %zu left to redo\n", (long long)n_loci, t1, t3, t2, t4,
+                h_cnt[0], redo.size());
+    return STRK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // integer issue-rate micro-benchmark (roofline denominator)
 // ------------------------------------------------------------------------------------------------
 extern "C" int strk_measure_int_peak(strk_ctx *ctx, double out_tiops[3]) {
     if (!ctx || !out_tiops) return set_err(STRK_ERR_ARG, "strk_measure_int_peak: null argument");
     CU(cudaSetDevice(ctx->device));
-    int *d_out = nullptr;
-    CU(cudaMalloc((void **)&d_out, sizeof(int)));
+    int *d_out = (int *)(ctx->d_queue + 7);  // context-owned scratch word and events: nothing to release on an error path
     const int grid = ctx->n_sm * 8, threads = 256, iters = 4096;
     const double instr = (double)grid * threads * (double)iters * 64.0;  // lane-level integer instructions
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1];
     for (int mode = 0; mode < 3; ++mode) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
@@ -1777,9 +2083,6 @@ extern "C" int strk_measure_int_peak(strk_ctx *ctx, double out_tiops[3]) {
         }
         out_tiops[mode] = instr / ((double)best * 1e-3) / 1e12;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d_out);
     return STRK_OK;
 }
 

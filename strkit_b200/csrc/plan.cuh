@@ -41,7 +41,7 @@ __global__ void plan_loci_kernel(const long long *__restrict__ read_begin, long 
     }
     if (motif_len[l] <= 0)
         plan_report(st, l, PLAN_ERR_MOTIF_EMPTY);
-    else if (motif_off[l] + (unsigned long long)motif_len[l] > arena_bytes)
+    else if (motif_off[l] > arena_bytes || (unsigned long long)motif_len[l] > arena_bytes - motif_off[l])
         plan_report(st, l, PLAN_ERR_MOTIF_PAST_ARENA);
     for (long long r = r0; r < r1; ++r) read_locus[r] = (int)l;
 }
@@ -69,10 +69,10 @@ __global__ void plan_reads_scan_kernel(const unsigned long long *__restrict__ se
             plan_report(st, r, PLAN_ERR_EMPTY);
         else if (n1 > (1 << 24))
             plan_report(st, r, PLAN_ERR_TOO_LONG);
-        else if (seq_off[r] + (unsigned long long)n1 > arena_bytes)
+        else if (seq_off[r] > arena_bytes || (unsigned long long)n1 > arena_bytes - seq_off[r])  // (no wrap-around)
             plan_report(st, r, PLAN_ERR_PAST_ARENA);
-        else if (est < 0 || est > (1 << 22))
-            plan_report(st, r, PLAN_ERR_EST);
+        else if (est < 0 || est > (1 << 22) || (long long)motif_len[read_locus[r]] * (long long)est > (1ll << 24))
+            plan_report(st, r, PLAN_ERR_EST);  // candidate columns (64-bit): a garbage estimate must not size scratch
         else {
             const int m = motif_len[read_locus[r]];
             int R = packed_ok ? strk_pick_rows_packed((int)n1 + 1) : 0;

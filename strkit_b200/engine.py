@@ -2,7 +2,6 @@
 from __future__ import annotations
 
 import collections
-import contextlib
 import ctypes as C
 import os
 import threading
@@ -77,7 +76,8 @@ class Engine:
     @property
     def total_launches(self) -> int:
         """Kernels launched by count_reads_stream on this GPU so far (both contexts)."""
-        return self.launches + (self._twin.launches if self._twin else 0)
+        return (self.launches + (self._twin.launches if self._twin else 0) +
+                sum(e.launches for e in (getattr(self, "_ref_engs", None) or [])))
 
     def sync(self) -> None:
         """Wait for everything queued on the context's streams (strk_sync)."""
@@ -86,6 +86,12 @@ class Engine:
             self._twin.sync()
 
     def close(self) -> None:
+        if getattr(self, "_aux_pool", None):
+            self._aux_pool.shutdown(wait=True)
+            self._aux_pool = None
+        for e in getattr(self, "_ref_engs", None) or []:
+            e.close()
+        self._ref_engs = None
         if getattr(self, "_twin", None):
             self._twin.close()
             self._twin = None
@@ -144,7 +150,7 @@ class Engine:
         """fill (H2D + device-side planning) -> run (kernels) -> download (D2H) on this context's reusable batch.
         Only the run phase holds `run_lock`: the copies of one block overlap the kernels of the other context.
         ref = (ref_batch, start_count, ref_size, rc[n, 3], vcf_anchor_size, out[n, 8]): the block's reference windows
-        (get_ref_repeat_count, once per locus) go through strk_ref_counts in the same run phase."""
+        (get_ref_repeat_count, once per locus) go through strk_ref_counts between the fill and the run phase."""
         if self._stream_batch is None:
             h = C.c_void_p()
             check(lib.strk_batch_create(self._ctx, C.byref(h)))
@@ -155,12 +161,13 @@ class Engine:
         if ref is not None:
             # Outside the run lock on purpose: the reference windows of block i + 1 (many small launches, a tenth of the
             # block's cells) run while the other context is in the read kernels of block i and fill the slots those
-            # leave idle at the tails of their launches (STRK_REF_IN_LOCK=1 restores the serial order: measurement only).
+            # leave idle at the tails of their launches.  (Measured against the alternatives: inside the lock 50.4 M
+            # reads x loci/s, here ~60 M, on a third context from a thread of its own 56.2 M, on two of those 57.8 M --
+            # under the persistent read CTAs a reference block is latency-bound, and this thread has the slack.)
             rb, start, ref_size, rc, anchor, ref_out = ref
-            with run_lock if os.environ.get("STRK_REF_IN_LOCK") else contextlib.nullcontext():
-                check(lib.strk_ref_counts(self._ctx, _p(rb.arena), rb.arena.nbytes, _p(rb.seq_off), _p(rb.lens), _p(start),
-                                          _p(ref_size), _p(rc), rb.n_loci, _p(rb.motif_off), _p(rb.motif_len), anchor, 0,
-                                          _p(ref_out)))
+            check(lib.strk_ref_counts(self._ctx, _p(rb.arena), rb.arena.nbytes, _p(rb.seq_off), _p(rb.lens), _p(start),
+                                      _p(ref_size), _p(rc), rb.n_loci, _p(rb.motif_off), _p(rb.motif_len), anchor, 0,
+                                      _p(ref_out)))
             self.launches += int(self.stats()["kernel_launches"])
         with run_lock:
             check(lib.strk_batch_run(self._ctx, self._stream_batch, rc_params.max_iters,
@@ -233,18 +240,39 @@ class Engine:
         return out, out_off
 
     def ref_counts(self, batch: ReadBatch, start_count, ref_size, rc_params, vcf_anchor_size: int,
-                   respect_coords: bool = False) -> np.ndarray:
+                   respect_coords: bool = False, out: np.ndarray | None = None) -> np.ndarray:
         """get_ref_repeat_count for every locus of a reference batch; rc_params int32 [n_loci, 3]."""
         batch.validate()
         _ascii_only(batch)
         start_count = np.ascontiguousarray(start_count, dtype=np.int32)
         ref_size = np.ascontiguousarray(ref_size, dtype=np.int32)
         rc = np.ascontiguousarray(rc_params, dtype=np.int32).reshape(batch.n_loci, 3)
-        out = np.empty((batch.n_loci, 8), dtype=np.int32)
+        if out is None:
+            out = np.empty((batch.n_loci, 8), dtype=np.int32)
         check(lib.strk_ref_counts(self._ctx, _p(batch.arena), batch.arena.nbytes, _p(batch.seq_off), _p(batch.lens),
                                   _p(start_count), _p(ref_size), _p(rc), batch.n_loci, _p(batch.motif_off),
                                   _p(batch.motif_len), vcf_anchor_size, int(respect_coords), _p(out)))
         return out
+
+    def ref_counts_async(self, batch: ReadBatch, start_count, ref_size, rc_params, vcf_anchor_size: int,
+                         respect_coords: bool = False, out_buf: np.ndarray | None = None):
+        """ref_counts on a native context of its own, from a helper thread: returns a Future of (out, stats).
+        A block's reference windows (a tenth of its cells, many small launches) then run UNDER the read kernels the
+        caller launches meanwhile on this context (Engine.run / count_reads) instead of before them."""
+        if getattr(self, "_ref_engs", None) is None:
+            d, ef, tf, mat, go, ge = self._init_args
+            self._ref_engs = [Engine(d, ef, tf, mat, go, ge)]   # a context of its own (the streamed path keeps two for reads)
+            self._aux_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="strk-ref")
+        ref_eng = self._ref_engs[0]
+
+        def job():
+            with ref_eng.lock:
+                out = ref_eng.ref_counts(batch, start_count, ref_size, rc_params, vcf_anchor_size, respect_coords, out=out_buf)
+                st = ref_eng.stats()
+                ref_eng.launches += int(st["kernel_launches"])
+            return out, st
+
+        return self._aux_pool.submit(job)
 
     def measure_int_peak(self) -> dict[str, float]:
         """Measured integer issue rates (1e12 lane-instructions/s): the DP kernels' roofline denominator."""

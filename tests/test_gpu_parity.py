@@ -386,6 +386,15 @@ def test_invalid_inputs_raise(sb):
     b.motif_len[0] = 0
     with pytest.raises(StrkError):
         eng.count_reads(b, p)
+    b = families_to_batch([("CAG", "CAGCAG" * 40, "AC", "GT")] * 600, est=[40] * 599 + [1 << 23])   # garbage estimate
+    with pytest.raises(StrkError, match="est_cn"):
+        eng.count_reads(b, p)                     # (device-side planning: more than 512 reads)
+    with pytest.raises(StrkError, match="est_cn"):
+        eng.count_reads(families_to_batch([("CAGCAG", "CAGCAG", "AC", "GT")], est=[(1 << 22) - 1]), p)  # m * est > 2^24
+    b = families_to_batch([("CAG", "CAGCAG", "AC", "GT")])
+    b.seq_off[0] = np.uint64(2 ** 64 - 4)        # offset + length wraps around 64 bits
+    with pytest.raises(StrkError, match="arena"):
+        eng.count_reads(b, p)
     with pytest.raises(StrkError):
         sb.Engine(gap_open=7, gap_extend=1)  # affine gaps are not what the reference uses
     with pytest.raises(NotImplementedError):
