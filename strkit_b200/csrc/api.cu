@@ -146,6 +146,7 @@ struct strk_batch {
     // identical reads of a locus share one table (dedupe.cuh): rep[r] = the read whose row r uses
     DevBuf<unsigned long long> hash;
     DevBuf<int> rep;
+    DevBuf<double> hint;  // per locus {smallest, largest} carried-offset fraction seen at a window miss (strk_slot_window)
     int *d_rep = nullptr;
     long long n_dup = 0;
     int max_n1 = 0, mb_cols_base = 0, mb_m = 0;
@@ -160,7 +161,7 @@ struct strk_batch {
     void release() {
         arena.release(), status.release(), seq_off.release(), motif_off.release(), lens.release(), est.release();
         motif_len.release(), read_locus.release(), order.release(), out.release(), read_begin.release();
-        bin.release(), hash.release(), rep.release(), arena4.release();
+        bin.release(), hash.release(), rep.release(), arena4.release(), hint.release();
     }
 };
 
@@ -289,6 +290,7 @@ extern "C" int strk_init(int device, const int8_t matrix[STRK_NSYM * STRK_NSYM],
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least, hi = greatest (numerically smaller)
+        if (getenv("STRK_NO_PRIORITY")) hi = lo;          // (measurement only: every stream at the default priority)
         ctx->prio_hi = hi;
         CU(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&ctx->fill_stream, cudaStreamNonBlocking, lo));
@@ -1051,19 +1053,41 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
     float ms_dp = 0.f, ms_replay = 0.f;
     double acc[2] = {0, 0};  // [0] reference-equivalent cells, [1] executed cells
 
+    // Where a widening pass has to look: per locus the carried-offset fractions its misses happened at (strk_slot_window)
+    if (b->hint.reserve(2 * (size_t)(b->n_loci ? b->n_loci : 1)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(STRK_ERR_NOMEM, "cannot allocate the window hints");
+    }
+    CU(cudaMemsetAsync(b->hint.p, 0, 2 * (size_t)b->n_loci * sizeof(double), st));
+
     for (int pass = 0;; ++pass) {
         if (wd > wd_cap) wd = wd_cap;
-        const int W = 2 * strk_read_wd(wd, 1, ws) + 1;  // table stride: the widest per-read window
+        const int threads = 256;
+        const double *d_hint = pass ? b->hint.p : nullptr;
+        int W = 2 * strk_read_wd(wd, 1, ws) + 1;  // table stride: the widest per-read window
+        if (pass) {
+            // windows of a widening pass are stretched towards the starts the locus' offset has produced: measure the widest
+            CU(cudaMemsetAsync(ctx->d_queue + 6, 0, sizeof(unsigned int), st));
+            plan_reads_kernel<<<(unsigned)((n_slots + threads - 1) / threads), threads, 0, st>>>(
+                d_read_ids, n_slots, b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_off, b->d_motif_len, wd, ws,
+                W, ctx->fams.p, ctx->d_acc + 1, nullptr, d_hint, ctx->d_queue + 6);
+            CU(cudaGetLastError());
+            unsigned int w_needed = 0;
+            CU(cudaMemcpyAsync(&w_needed, ctx->d_queue + 6, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if ((int)w_needed > W) W = (int)w_needed;
+            if (W > STRK_MAX_WINDOW)
+                return set_err(STRK_ERR_SEARCH, "search left the widest supported window (%d sizes)", STRK_MAX_WINDOW);
+        }
         if (ctx->fams.reserve((size_t)n_slots) != cudaSuccess || ctx->table.reserve((size_t)n_slots * (size_t)W) != cudaSuccess) {
             cudaGetLastError();
             return set_err(STRK_ERR_NOMEM, "cannot allocate score tables for %lld reads x %d sizes", n_slots, W);
         }
         int b_len, rowlen;
-        scratch_dims(b, strk_read_wd(wd, 1, ws), &b_len, &rowlen);
-        const int threads = 256;
+        scratch_dims(b, pass ? W : strk_read_wd(wd, 1, ws), &b_len, &rowlen);  // (n_hi - est <= W in a stretched window)
         plan_reads_kernel<<<(unsigned)((n_slots + threads - 1) / threads), threads, 0, st>>>(
             d_read_ids, n_slots, b->d_seq_off, b->d_lens, b->d_est, b->d_read_locus, b->d_motif_off, b->d_motif_len, wd,
-            ws, W, ctx->fams.p, ctx->d_acc + 1, pass == 0 ? b->d_rep : nullptr);
+            ws, W, ctx->fams.p, ctx->d_acc + 1, pass == 0 ? b->d_rep : nullptr, d_hint);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[0], st));
@@ -1149,12 +1173,12 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
             replay_reads_small_kernel<<<(unsigned)((n_list + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, 0, st>>>(
                 ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
                 b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
-                ctx->d_queue + 1, ctx->d_acc, pass == 0 ? b->d_rep : nullptr);
+                ctx->d_queue + 1, ctx->d_acc, pass == 0 ? b->d_rep : nullptr, b->hint.p);
         else
             replay_reads_kernel<<<(unsigned)((n_list + 127) / 128), 128, 0, st>>>(
                 ctx->table.p, W, wd, ws, d_locus_ids, d_slot_begin, (int)n_list, b->d_read_begin, b->d_est, b->d_lens,
                 b->d_motif_len, max_iters, local_search_range, step_size, ctx->tie_flags, b->d_out, b->d_status,
-                ctx->d_queue + 1, ctx->d_acc, pass == 0 ? b->d_rep : nullptr);
+                ctx->d_queue + 1, ctx->d_acc, pass == 0 ? b->d_rep : nullptr, b->hint.p);
         CU(cudaGetLastError());
         ctx->stats[2] += 1;
         CU(cudaEventRecord(ctx->ev[2], st));
@@ -1223,7 +1247,9 @@ extern "C" int strk_batch_run(strk_ctx *ctx, strk_batch *b, int max_iters, int l
         d_read_ids = ctx->list_a.p;
         d_locus_ids = ctx->list_b.p;
         d_slot_begin = ctx->list_c.p;
-        int widen = pass == 0 ? 4 : 8;  // most second passes need a few more sizes, the rest are far off
+        // The next pass looks where the misses happened (hints) with twice the margin; once that has not been enough twice
+        // it widens 8x per pass like the blind scheme did (a search that goes nowhere near its start or its estimate).
+        int widen = pass < 2 ? 2 : 8;
         if (const char *env = getenv("STRK_WIDEN1")) widen = pass == 0 && atoi(env) >= 2 ? atoi(env) : widen;  // tuning only
         wd *= widen;
     }

@@ -229,8 +229,10 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
                                     const int *__restrict__ lens, const int *__restrict__ motif_len, int max_iters,
                                     int range, int step, int tie_flags, int *__restrict__ out,
                                     unsigned char *__restrict__ locus_status, unsigned int *miss_count,
-                                    double *ref_cells, const int *__restrict__ rep) {
+                                    double *ref_cells, const int *__restrict__ rep, double *__restrict__ hint = nullptr) {
     // rep != nullptr (first pass only, slot == read): read r looks its scores up in the row of read rep[r]
+    // hint != nullptr (widening passes): per locus {smallest, largest} offset fraction seen at a miss (strk_slot_window);
+    // a locus that misses again adds the fraction it missed at
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_list) return;
     const int locus = locus_ids ? locus_ids[q] : q;
@@ -251,12 +253,18 @@ __global__ void replay_reads_kernel(const int *__restrict__ table, int W, int wd
             frac = 0.0;  // :1133
         else
             read_sc += off;  // :1136
-        const int n_lo = est - wdr > 0 ? est - wdr : 0;
-        const int n_hi = est + wdr;
+        int n_lo, n_hi;
+        strk_slot_window(est, m, wd, wide_short, hint ? hint + 2 * (size_t)locus : nullptr, n_lo, n_hi);
         ClimbResult cr = climb_single(table + (size_t)(rep ? (long long)rep[r] : slot) * (size_t)W, n_lo, n_hi, read_sc,
                                       max_iters, range, step, tie_flags, seen);
         if (cr.status) {
             status = cr.status;
+            if (hint && cr.status == 1) {  // where the next pass has to look: the fraction this read started from
+                double *h = hint + 2 * (size_t)locus;
+                const double fr_used = read_sc == est ? 0.0 : frac;
+                h[0] = fr_used < h[0] ? fr_used : h[0];
+                h[1] = fr_used > h[1] ? fr_used : h[1];
+            }
             break;
         }
         margin_used |= cr.lo_touched < est - wd || cr.hi_touched > est + wd;
@@ -289,7 +297,9 @@ __global__ void __launch_bounds__(REPLAY_THREADS)
                               const long long *__restrict__ read_begin, const int *__restrict__ est_cn,
                               const int *__restrict__ lens, const int *__restrict__ motif_len, int max_iters, int range,
                               int step, int tie_flags, int *__restrict__ out, unsigned char *__restrict__ locus_status,
-                              unsigned int *miss_count, double *ref_cells, const int *__restrict__ rep) {
+                              unsigned int *miss_count, double *ref_cells, const int *__restrict__ rep,
+                              double *__restrict__ hint = nullptr) {
+    // hint != nullptr: a locus that misses records the offset fraction it missed at (first pass: windows are est +- wdr)
     __shared__ int rows[REPLAY_THREADS * (REPLAY_WMAX + 1)];
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_list) return;
@@ -330,6 +340,12 @@ __global__ void __launch_bounds__(REPLAY_THREADS)
         ClimbResult cr = climb_single(row, n_lo, n_hi, read_sc, max_iters, range, step, tie_flags, seen);
         if (cr.status) {
             status = cr.status;
+            if (hint && cr.status == 1) {
+                double *h = hint + 2 * (size_t)locus;
+                const double fr_used = read_sc == est ? 0.0 : frac;
+                h[0] = fr_used < h[0] ? fr_used : h[0];
+                h[1] = fr_used > h[1] ? fr_used : h[1];
+            }
             break;
         }
         margin_used |= cr.lo_touched < est - wd || cr.hi_touched > est + wd;
@@ -353,7 +369,9 @@ __global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_
                                   const int *__restrict__ est_cn, const int *__restrict__ read_locus,
                                   const unsigned long long *__restrict__ motif_off, const int *__restrict__ motif_len,
                                   int wd, int wide_short, int W, FamDesc *__restrict__ fams, double *exec_cells,
-                                  const int *__restrict__ rep) {
+                                  const int *__restrict__ rep, const double *__restrict__ hint = nullptr,
+                                  unsigned int *w_needed = nullptr) {
+    // w_needed != nullptr: only measure -- the widest window of the pass (atomicMax), no descriptor is written
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cells = 0.0;
     if (s < n_slots) {
@@ -368,13 +386,15 @@ __global__ void plan_reads_kernel(const int *__restrict__ read_ids, long long n_
     f.n_fr = lens[3 * r + 2];
     f.m = motif_len[locus];
     const int est = est_cn[r];
-    const int wdr = strk_read_wd(wd, f.m, wide_short);
-    f.n_lo = est - wdr > 0 ? est - wdr : 0;
-    f.n_hi = est + wdr;
-    fams[s] = f;
-    // executed DP cells: one forward sweep over fl + motif*n_hi plus one backward sweep over fr
-    if (!rep || rep[r] == (int)r)  // a read that shares another read's table executes no cells
-        cells = (double)(f.n_fl + f.n_tr + f.n_fr) * ((double)f.n_fl + (double)f.m * (double)f.n_hi + (double)f.n_fr);
+    strk_slot_window(est, f.m, wd, wide_short, hint ? hint + 2 * (size_t)locus : nullptr, f.n_lo, f.n_hi);
+    if (w_needed) {
+        atomicMax(w_needed, (unsigned int)(f.n_hi - f.n_lo + 1));
+    } else {
+        fams[s] = f;
+        // executed DP cells: one forward sweep over fl + motif*n_hi plus one backward sweep over fr
+        if (!rep || rep[r] == (int)r)  // a read that shares another read's table executes no cells
+            cells = (double)(f.n_fl + f.n_tr + f.n_fr) * ((double)f.n_fl + (double)f.m * (double)f.n_hi + (double)f.n_fr);
+    }
     }
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
     if ((threadIdx.x & 31) == 0 && cells > 0.0) atomicAdd(exec_cells, cells);

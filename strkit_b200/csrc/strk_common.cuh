@@ -1,6 +1,7 @@
 // strk_common.cuh -- shared device/host definitions for the B200 repeat-count kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #define STRK_WARP 32
@@ -47,6 +48,29 @@ struct ScoreConsts {
 // +-6 window at 29 % of the 2-mer loci, 4 % of the 3-mers, 1 % of the 4-mers; none at +-8 / +-8 / +-7).
 __host__ __device__ inline int strk_read_wd(int wd, int m, int wide_short) {
     return wd + (wide_short ? (m <= 3 ? 2 : (m == 4 ? 1 : 0)) : 0);
+}
+
+// Score window [lo, hi] (candidate sizes) of one read in a pass.  First pass (hint == nullptr): est +- wdr.  Widening
+// passes: the start count of a read is its estimate plus a carried offset, round(frac * est) (call_locus.py:1129-1136),
+// and on loci whose reads alternate between a short and an expanded allele that offset is tens of copies -- so the
+// window is stretched towards the starts the locus' offset fraction has been seen to produce so far (hint[0] = smallest,
+// hint[1] = largest fraction at a miss) instead of being widened blindly around the estimate: a 6 kb expansion that
+// starts 75 copies off needs ~100 sizes, not 385.  Used by the table planner and by the replay: they must agree.
+__host__ __device__ inline void strk_slot_window(int est, int m, int wd, int wide_short, const double *hint, int &lo, int &hi) {
+    const int wdr = strk_read_wd(wd, m, wide_short);
+    int s_lo = 0, s_hi = 0;
+    if (hint) {
+        const double a = rint(hint[0] * (double)est), b = rint(hint[1] * (double)est);
+        // (an offset below -est is dropped by the reference: the read starts at its estimate)
+        const int ia = a < -(double)est ? 0 : (int)a, ib = b < -(double)est ? 0 : (int)b;
+        s_lo = ia < ib ? ia : ib;
+        s_hi = ia < ib ? ib : ia;
+        if (s_lo > 0) s_lo = 0;
+        if (s_hi < 0) s_hi = 0;
+    }
+    lo = est + s_lo - wdr;
+    if (lo < 0) lo = 0;
+    hi = est + s_hi + wdr;
 }
 
 // rows per lane of the packed kernel (32*R >= n1, every R in 2..16 is instantiated); 0 = too long for it
