@@ -130,7 +130,7 @@ def ncu_dram_traffic():
     `ncu --set full` summary (profiles/, a separate run under the profiler; None if the file is not there)."""
     import re
 
-    path = os.path.join(ROOT, "profiles", "r1_full_packed_v9.txt")
+    path = os.path.join(ROOT, "profiles", "r2_full_packed_r10.txt")
     if not os.path.exists(path):
         return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -143,7 +143,7 @@ def ncu_dram_traffic():
         m = re.match(r"dram__bytes_(read|write)\.sum\s+(\w+)\s+([0-9.]+)", line)
         if m and kernel is not None:
             total += float(m.group(3)) * unit.get(m.group(2), 1.0)
-    return (total or None), f"{kernel}, one launch, profiles/r1_full_packed_v9.txt"
+    return (total or None), f"{kernel}, one launch, profiles/r2_full_packed_r10.txt"
 
 
 def cpu_baseline(batch, n_loci_sample, steps=1):

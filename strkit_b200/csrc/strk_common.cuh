@@ -82,10 +82,14 @@ __host__ __device__ inline int strk_pick_rows_packed(int n1) {
     return r <= STRK_PK_RMAX ? r : 0;
 }
 
-__host__ __device__ inline int strk_pick_rows(int n1) {
+__host__ __device__ inline int strk_pick_rows(int n1, int warps = 4) {
     // rows per lane of the strip layout: smallest R in the instantiated set with 32*R >= n1
     const int set[12] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16};
     for (int k = 0; k < 12; ++k)
         if (32 * set[k] >= n1) return set[k];
+    // Several strips (pipelined over the warps of a CTA): R = 16.  A cost model that trades rounds of the pipeline
+    // against the step length (e.g. 11 strips of 384 rows instead of 9 of 512 for a 4 140-row window) was measured on
+    // config 4 and lost 8 %: every additional strip adds its own hand-over lag and synchronisation.
+    (void)warps;
     return 16;
 }
