@@ -411,18 +411,54 @@ static int validate_motifs(const char *who, uint64_t arena_bytes, const uint64_t
 // ------------------------------------------------------------------------------------------------
 // general DP launch
 // ------------------------------------------------------------------------------------------------
-// One family per CTA of GEN_WARPS warps (dp_general.cuh): the strips of a long read run as a pipeline over the warps.
-static const int GEN_THREADS = GEN_WARPS * 32;
-
-static int general_grid(strk_ctx *ctx, long long n_fams) {
-    long long blocks = n_fams;
-    long long cap = (long long)ctx->n_sm * (16 / GEN_WARPS);  // persistent: 16 warps per SM (128 registers per thread)
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
+// One family per CTA (dp_general.cuh): the strips of a long read run as a pipeline over the warps of the CTA.
+// Throughput shape: GEN_WARPS warps per CTA, 16 / GEN_WARPS CTAs per SM (128 registers per thread).
+// Latency shape: a launch that holds long (multi-strip) reads but no more families than fit the SMs at 8 warps each -- a
+// locus or a few per call, the widening passes of a block of expansions -- is bound by the time of ONE read; there a
+// CTA runs 8 warps, so that twice as many strips of a read are in flight.  Measured on 21 reads of 6 147 rows
+// (profiles/r2_general_latency_shape.txt): 2.96 ms at 4 warps, 2.36 ms at 8, 2.52 ms at 16 -- a warp alone on its
+// scheduler issues one instruction per 3.7 cycles (dependent issue), and beyond 2 warps per scheduler the strips of one
+// read contend for the same issue slots and ALU pipe, so the gain stops at 8.
+static int general_latency_warps() {  // (STRK_GEN_LATENCY_WARPS: measurement switch)
+    static const int w = getenv("STRK_GEN_LATENCY_WARPS") ? atoi(getenv("STRK_GEN_LATENCY_WARPS")) : 8;
+    return std::min(std::max(w, GEN_WARPS), GEN_WARPS_MAX);
 }
 
-// scratch: per CTA [b_len ints][GEN_RING rows of rowlen ints]
+struct GenShape {
+    int grid, warps;
+    size_t scratch;  // ints: per CTA [b_len][warps + 1 boundary rows of rowlen]
+};
+
+static GenShape general_shape(strk_ctx *ctx, long long n_fams, int b_len, int rowlen, bool latency) {
+    GenShape g;
+    g.warps = latency ? general_latency_warps() : GEN_WARPS;
+    long long blocks = n_fams;
+    const long long cap = (long long)ctx->n_sm * (16 / g.warps);  // persistent
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    g.grid = (int)blocks;
+    g.scratch = ((size_t)b_len + (size_t)(g.warps + 1) * (size_t)rowlen) * (size_t)g.grid;
+    return g;
+}
+
+// most families a launch may hold and still take the latency shape (STRK_GEN_LATENCY_MAX: measurement switch)
+static long long lat_max(strk_ctx *ctx) {
+    static const long long env = getenv("STRK_GEN_LATENCY_MAX") ? atoll(getenv("STRK_GEN_LATENCY_MAX")) : -1;
+    return env >= 0 ? env : (long long)ctx->n_sm * (16 / general_latency_warps());  // one wave of latency-shape CTAs
+}
+
+static bool general_latency_mode(strk_ctx *ctx, long long n_fams, int rowlen, bool dev_count) {
+    static const bool off = getenv("STRK_GEN_LATENCY") && atoi(getenv("STRK_GEN_LATENCY")) == 0;  // (measurement switch)
+    return !off && !dev_count && rowlen > 2 && n_fams <= lat_max(ctx);
+}
+
+// scratch that any general launch of up to n_fams families may need (either shape)
+static size_t general_scratch_max(strk_ctx *ctx, long long n_fams, int b_len, int rowlen) {
+    size_t a = general_shape(ctx, n_fams, b_len, rowlen, false).scratch;
+    if (rowlen > 2) a = std::max(a, general_shape(ctx, std::min(n_fams, lat_max(ctx)), b_len, rowlen, true).scratch);
+    return a;
+}
+
 static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const int *d_order, long long n_fams,
                           const unsigned char *d_arena, void *d_table, int b_len, int rowlen, cudaStream_t st,
                           const unsigned int *d_count = nullptr) {
@@ -430,9 +466,9 @@ static int launch_general(strk_ctx *ctx, bool ref, const FamDesc *d_fams, const 
     if (n_fams <= 0) return STRK_OK;
     if (d_count && n_fams > (long long)ctx->n_sm * 4) n_fams = (long long)ctx->n_sm * 4;
     if (n_fams > 0x7fffffffLL) return set_err(STRK_ERR_ARG, "too many families in one launch");
-    const int grid = general_grid(ctx, n_fams);
-    const size_t per_cta = (size_t)b_len + (size_t)GEN_RING * (size_t)rowlen;
-    const size_t total = per_cta * (size_t)grid;
+    const GenShape gs = general_shape(ctx, n_fams, b_len, rowlen, general_latency_mode(ctx, n_fams, rowlen, d_count != nullptr));
+    const int grid = gs.grid, GEN_THREADS = gs.warps * 32;
+    const size_t total = gs.scratch;
     if (ctx->scratch.reserve(total) != cudaSuccess) {
         cudaGetLastError();
         return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of DP scratch", total * sizeof(int));
@@ -665,7 +701,7 @@ static int launch_pass(strk_ctx *ctx, const int *const *list, const long long *c
         // scratch of the largest general launch of this pass, reserved before anything is in flight
         long long fams_max = std::max(cnt[0], std::min(packed_total, (long long)ctx->n_sm * 4));
         for (int k = 1; k < STRK_PK_NBIN; ++k) fams_max = std::max(fams_max, cnt[k]);
-        const size_t total = ((size_t)b_len + (size_t)GEN_RING * (size_t)rowlen) * (size_t)general_grid(ctx, fams_max);
+        const size_t total = general_scratch_max(ctx, fams_max, b_len, rowlen);
         if (ctx->scratch.reserve(total) != cudaSuccess) {
             cudaGetLastError();
             return set_err(STRK_ERR_NOMEM, "cannot allocate %zu bytes of DP scratch", total * sizeof(int));

@@ -45,22 +45,24 @@ struct PassCfg {
                           // starts inside the suffix columns (free s2 begin), see dp_pass
     int *out;             // COMBINE: [n_hi - n_lo + 1], pre-set to STRK_NEG_INF
     long long *out64;     // ARGMAX: packed (score << 32 | 0x7fffffff - row), pre-set to LLONG_MIN
-    int *rows;            // boundary-row scratch: GEN_RING rows of rowlen ints (multi-strip families only)
+    int *rows;            // boundary-row scratch: (warps of the CTA + 1) rows of rowlen ints (multi-strip families only)
     int rowlen;
 };
 
 // A family is swept by the GEN_WARPS warps of one CTA: warp w takes the strips w, w + GEN_WARPS, ... and the strips
 // run as a pipeline -- strip b + 1 follows strip b about 64 columns behind, reading the boundary row strip b leaves
-// in the ring slot b % GEN_RING.  A long read (config 4: 12 strips of 6 200 columns) is bound by the latency of its
+// in the ring slot b % (warps + 1).  A long read (config 4: 12 strips of 6 200 columns) is bound by the latency of its
 // own dependency chain, so four strips in flight cut its time almost four-fold.  progress[slot] = b * stride + last
 // column written: values only grow over the strips that reuse a slot, so a stale value never satisfies a waiter.
 #ifndef GEN_WARPS
 #define GEN_WARPS 4
 #endif
-#define GEN_RING (GEN_WARPS + 1)
-#define GEN_FAST_MMAX 256  // longest motif the steady-state loop of dp_pass takes (longer ones: the general loop only)
+#define GEN_WARPS_MAX 16  // most warps a CTA may be launched with (512 threads x 128 registers = one SM's file)
+#define GEN_RING_MAX (GEN_WARPS_MAX + 1)  // ring of boundary rows / progress counters: (warps of the CTA) + 1 slots in use
+#define GEN_FAST_MMAX 256  // longest motif / prefix (flank) whose column tables a sweep keeps in shared memory; longer
+#define GEN_FAST_PMAX 256  // ones take the general loop with a symbol fetch per column
 struct GenSync {
-    volatile long long progress[GEN_RING];
+    volatile long long progress[GEN_RING_MAX];
     unsigned int q;
 };
 
@@ -86,9 +88,11 @@ struct GenSmem {
     unsigned long long t8[STRK_NSYM_];         // PRMT byte table per column symbol: byte c = score(row class c) + 2g
     unsigned char cls[STRK_SMAT_ROWS + 1];     // row symbol -> PRMT class (A C G T N X other pad), 0x80 = none
     unsigned one;                              // = 1, opaque to the compiler: multiplier of the FMA-pipe adds
-    // byte tables of the motif columns of the sweep in progress, in sweep order (tM[k] = t8[symbol of the k-th column of
-    // a motif copy]): the steady-state loop of dp_pass fetches its column table with one LDS.64 and a wrapping offset
-    unsigned long long tM[2][GEN_FAST_MMAX];  // [1]: the second of two sweeps that run side by side (process_ref_family)
+    // byte tables of the columns of the sweep in progress, in sweep order: [0, n_pre) the prefix (flank) columns, then
+    // the m columns of one motif copy (tC[n_pre + k] = t8[symbol of the k-th column of a copy]).  A lane walks it with
+    // one LDS.64 per step and an offset that wraps from the end of the copy back to its start -- no symbol fetch
+    // (global load -> code table -> byte table, a chain of three loads) on the critical path of a step.
+    unsigned long long tC[2][GEN_FAST_PMAX + GEN_FAST_MMAX];  // [1]: second of two side-by-side sweeps (process_ref_family)
 };
 
 __device__ __forceinline__ int gen_add(int a, int b, unsigned one) {  // a + b as IMAD (FMA pipe)
@@ -102,8 +106,8 @@ __device__ __forceinline__ unsigned gen_prmt(unsigned a, unsigned b, unsigned se
     return r;
 }
 
-// Steady-state steps of a sweep: every lane is inside the matrix, every lane's column is a motif column, and no lane can
-// reach a candidate column -- for a 6 kb expansion that is ~95 % of the steps.  What is left of the general loop's
+// Steady-state steps of a sweep: every lane is inside the matrix and no lane can reach a candidate column -- for a 6 kb
+// expansion that is ~97 % of the steps.  What is left of the general loop's
 // bookkeeping: one LDS.64 of the column's byte table with a wrapping offset, the two shuffles, the boundary-row
 // store of lane 31 and the running maximum of the last row; everything else (column fetch with its flank / motif /
 // reverse cases, activity tests, candidate detection) is compiled out.  TOP / BOT / PM are uniform per strip.
@@ -111,16 +115,15 @@ __device__ __forceinline__ unsigned gen_prmt(unsigned a, unsigned b, unsigned se
 //   PM:  the running maximum of the last row is needed (last strip, free s2 end).
 template <int R, bool TOP, bool BOT, bool PM>
 __device__ __forceinline__ void gen_fast_steps(int (&H)[R], const unsigned (&sel)[R], int &prev_up, int &s, const int s_end,
-                                               const int lane, const unsigned one, const unsigned long long *tM, const int m,
-                                               int koff, int topv, const int tinc, int &top_cur, int &top_nxt,
+                                               const int lane, const unsigned one, const unsigned long long *tC, const int endb,
+                                               const int wrapb, int koff, int topv, const int tinc, int &top_cur, int &top_nxt,
                                                const int *__restrict__ top, int *__restrict__ bot, const int ncols,
                                                volatile long long *prog_in, volatile long long *prog_out,
                                                const long long stride, const int b, int &pmax, const int g) {
     // Whole chunks of 32 steps, entered with s a multiple of 32: the boundary-row refill (TOP) and the progress
     // publication (BOT) happen between chunks, the 32 steps in between are straight-line and convergent (lane 31's
     // boundary-row store is predicated, not branched).
-    const int mbytes = m * 8;
-    const char *tbase = (const char *)tM;
+    const char *tbase = (const char *)tC;  // koff: byte offset of this lane's column; endb -> wrapb at the end of a copy
     int gj = g * (s - lane + 1);  // g * (column of this lane)
     const unsigned on31 = lane == 31 ? 1u : 0u;
 #pragma unroll 1
@@ -147,7 +150,7 @@ __device__ __forceinline__ void gen_fast_steps(int (&H)[R], const unsigned (&sel
             }
             const unsigned long long t = *(const unsigned long long *)(tbase + koff);
             koff += 8;
-            koff = koff == mbytes ? 0 : koff;
+            koff = koff == endb ? wrapb : koff;
             const unsigned tlo = (unsigned)t, thi = (unsigned)(t >> 32);
             int d = prev_up, u = up_in;
             prev_up = up_in;
@@ -191,12 +194,16 @@ template <bool LUT>
 __device__ __forceinline__ bool dp_pass_open(const PassCfg &c, const GenSmem &sc, GenSync &sy, int slot, bool first) {
     if (first) {
         __syncthreads();  // the previous sweep of this family is complete (its B column, its boundary rows)
-        if (threadIdx.x < GEN_RING) sy.progress[threadIdx.x] = -1;
+        if (threadIdx.x < GEN_RING_MAX) sy.progress[threadIdx.x] = -1;
     }
-    const bool fast_ok = LUT && c.kind != PASS_DUMP && c.m <= GEN_FAST_MMAX;
-    if (fast_ok)
-        for (int k = threadIdx.x; k < c.m; k += blockDim.x)
-            const_cast<GenSmem &>(sc).tM[slot][k] = sc.t8[sc.lut[c.motif[c.rev_motif ? c.m - 1 - k : k]]];
+    const bool fast_ok = LUT && c.m <= GEN_FAST_MMAX && c.n_pre <= GEN_FAST_PMAX;
+    if (fast_ok) {
+        unsigned long long *t = const_cast<GenSmem &>(sc).tC[slot];
+        for (int k = threadIdx.x; k < c.n_pre; k += blockDim.x) t[k] = sc.t8[sc.lut[c.pre[c.rev_pre ? c.n_pre - 1 - k : k]]];
+        if (c.ncols > c.n_pre)  // (the backward sweep of a read family stops at the end of its prefix)
+            for (int k = threadIdx.x; k < c.m; k += blockDim.x)
+                t[c.n_pre + k] = sc.t8[sc.lut[c.motif[c.rev_motif ? c.m - 1 - k : k]]];
+    }
     return fast_ok;
 }
 
@@ -231,7 +238,8 @@ __device__ void dp_pass_body(const PassCfg &c, const GenSmem &sc, GenSync &sy, i
     }
 
     const long long stride = (long long)c.ncols + 2;
-    for (int b = warp; b < NB; b += GEN_WARPS) {
+    const int nw = (int)(blockDim.x >> 5), ring = nw + 1;  // (dp_pass_pair: one strip per sweep, nw is not used)
+    for (int b = warp; b < NB; b += nw) {
         const int Ibase = b * RB + lane * R;  // padded index of the row above my strip
         int H[R];
         unsigned sel[R];  // LUT: PRMT selector; else: row offset into smat2
@@ -245,10 +253,10 @@ __device__ void dp_pass_body(const PassCfg &c, const GenSmem &sc, GenSync &sy, i
         }
         int prev_up = Ibase - off >= 1 ? border_col0(c, Ibase - off, g) + g * Ibase : g * off;  // row above, column 0
         // (a sweep without columns computes no cell: nothing is published, nothing may be waited for)
-        const int *top = b == 0 || c.ncols == 0 ? nullptr : c.rows + (size_t)((b - 1) % GEN_RING) * c.rowlen;
-        int *bot = b < NB - 1 ? c.rows + (size_t)(b % GEN_RING) * c.rowlen : nullptr;
-        volatile long long *prog_in = &sy.progress[(b + GEN_RING - 1) % GEN_RING];
-        volatile long long *prog_out = &sy.progress[b % GEN_RING];
+        const int *top = b == 0 || c.ncols == 0 ? nullptr : c.rows + (size_t)((b - 1) % ring) * c.rowlen;
+        int *bot = b < NB - 1 ? c.rows + (size_t)(b % ring) * c.rowlen : nullptr;
+        volatile long long *prog_in = &sy.progress[(b + ring - 1) % ring];
+        volatile long long *prog_out = &sy.progress[b % ring];
         // wait until the strip above has published its boundary row up to column `col` (clipped to the last one)
         auto wait_top = [&](int col) {
             const long long need = (long long)(b - 1) * stride + (col < c.ncols ? col : c.ncols);
@@ -269,33 +277,43 @@ __device__ void dp_pass_body(const PassCfg &c, const GenSmem &sc, GenSync &sy, i
         int kk_cur = -1, kk_nxt = -1;
         unsigned long long t_nxt = 0ull;
         int code_nxt = 0;
+        // fast_ok: the column tables of the sweep are in shared memory (sc.tC[slot]) and ko walks them
+        const char *tbase = (const char *)sc.tC[slot];
+        const int endb = (c.n_pre + c.m) * 8, wrapb = c.n_pre * 8;
+        int ko = 0;  // byte offset of the next column to fetch
         auto fetch = [&](int jn) {
             if (jn < 1 || jn > c.ncols) return;
-            if (jn <= c.n_pre) {
-                code_nxt = sc.lut[c.pre[c.rev_pre ? c.n_pre - jn : jn - 1]];
-            } else {
-                kk_nxt = kk_nxt + 1 == c.m ? 0 : kk_nxt + 1;
-                code_nxt = sc.lut[c.motif[c.rev_motif ? c.m - 1 - kk_nxt : kk_nxt]];
+            if (jn > c.n_pre) kk_nxt = kk_nxt + 1 == c.m ? 0 : kk_nxt + 1;
+            if (LUT && fast_ok) {
+                t_nxt = *(const unsigned long long *)(tbase + ko);
+                ko += 8;
+                ko = ko == endb ? wrapb : ko;
+                return;
             }
+            if (jn <= c.n_pre)
+                code_nxt = sc.lut[c.pre[c.rev_pre ? c.n_pre - jn : jn - 1]];
+            else
+                code_nxt = sc.lut[c.motif[c.rev_motif ? c.m - 1 - kk_nxt : kk_nxt]];
             if (LUT) t_nxt = sc.t8[code_nxt];
         };
         fetch(1 - lane);
         const int row0_bias = g * off;
         const int nsteps = c.ncols + 31;
-        // steady-state range [s_a, s_b): lane 31 is past the prefix columns (s - 30 > n_pre), lane 0 has not reached the
-        // first candidate column n_pre + m * n_lo (it does at step n_pre + m * n_lo - 1)
-        int s_a = (c.n_pre + 31 + 31) & ~31, s_b = c.n_pre + c.m * c.n_lo - 1;  // (whole 32-step chunks from a multiple of 32)
+        // steady-state range [s_a, s_b): every lane is inside the matrix (s >= 31), lane 0 has not reached the first
+        // candidate column (n_pre + m * n_lo, at step n_pre + m * n_lo - 1; the backward sweep: its last column)
+        int s_a = 32, s_b = c.kind == PASS_DUMP ? c.ncols - 1 : c.n_pre + c.m * c.n_lo - 1;  // (whole 32-step chunks)
         if (s_b > c.ncols - 1) s_b = c.ncols - 1;
-        s_b = s_a + ((s_b - s_a) & ~31);
-        if (!fast_ok || s_b - s_a < 64) s_a = s_b = nsteps;  // not worth it: one general loop
+        s_b = s_b < s_a ? s_a : s_a + ((s_b - s_a) & ~31);
+        if (!fast_ok || s_b - s_a < 32) s_a = s_b = nsteps;  // not worth it: one general loop
         for (int s = 0; s < nsteps; ++s) {
             if (LUT && s == s_a) {
-                const int koff = ((s - lane - c.n_pre) % c.m) * 8;  // column s - lane + 1 is motif column (j - n_pre - 1) % m
+                const int j0 = s - lane;  // columns before this lane's: j0 <= n_pre -> prefix entry j0, else motif entry
+                const int koff = (j0 < c.n_pre ? j0 : c.n_pre + (j0 - c.n_pre) % c.m) * 8;
                 const int topv = border_row0(c, s + 1, g) + row0_bias + g * (s + 1);
                 const int tinc = c.s2_beg_free ? g : 0;
                 const bool pm = b == NB - 1;  // (only read there; cheap enough to keep for every last strip)
 #define GEN_FAST(TOPF, BOTF, PMF)                                                                                       \
-    gen_fast_steps<R, TOPF, BOTF, PMF>(H, sel, prev_up, s, s_b, lane, one, sc.tM[slot], c.m, koff, topv, tinc, top_cur, top_nxt, \
+    gen_fast_steps<R, TOPF, BOTF, PMF>(H, sel, prev_up, s, s_b, lane, one, sc.tC[slot], endb, wrapb, koff, topv, tinc, top_cur, top_nxt, \
                                        top, bot, c.ncols, prog_in, prog_out, stride, b, pmax, g)
                 if (top) {
                     if (bot)
@@ -315,11 +333,15 @@ __device__ void dp_pass_body(const PassCfg &c, const GenSmem &sc, GenSync &sy, i
 #undef GEN_FAST
                 // back to the general loop at step s = s_b: restore its one-column-ahead fetch state and the count of
                 // motif copies this lane has completed (last computed column: s - lane)
-                const int jn = s - lane + 1;
-                kk_nxt = (jn - c.n_pre - 1) % c.m;
-                code_nxt = sc.lut[c.motif[c.rev_motif ? c.m - 1 - kk_nxt : kk_nxt]];
-                t_nxt = sc.t8[code_nxt];
-                ncop = (s - lane - c.n_pre) / c.m;
+                const int jn = s - lane + 1;  // (1 <= jn: s >= 31; jn may lie past the last column at the end of a sweep)
+                kk_nxt = jn > c.n_pre ? (jn - c.n_pre - 1) % c.m : -1;
+                ko = (jn <= c.n_pre ? jn - 1 : c.n_pre + kk_nxt) * 8;
+                if (jn <= c.ncols) {
+                    t_nxt = *(const unsigned long long *)(tbase + ko);
+                    ko += 8;
+                    ko = ko == endb ? wrapb : ko;
+                }
+                ncop = s - lane > c.n_pre ? (s - lane - c.n_pre) / c.m : 0;
                 if (s >= nsteps) break;
             }
             const int j = s - lane + 1;
@@ -583,7 +605,7 @@ __device__ void process_ref_family(const FamDesc &f, const unsigned char *arena,
 
 // Persistent kernel: CTAs (GEN_WARPS warps on one family) pull families from a cost-sorted queue.
 template <bool REF>
-__global__ void __launch_bounds__(GEN_WARPS * 32, 16 / GEN_WARPS) dp_general_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ order,
+__global__ void __launch_bounds__(GEN_WARPS_MAX * 32, 1) dp_general_kernel(const FamDesc *__restrict__ fams, const int *__restrict__ order,
                                                          int n_fams, const unsigned char *__restrict__ arena,
                                                          const ScoreConsts *__restrict__ consts, void *table,
                                                          int *scratch, int scratch_rowlen, int scratch_b_len,
@@ -601,7 +623,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32, 16 / GEN_WARPS) dp_general_ker
     if (threadIdx.x == 0) sc.one = consts->one_v[0];
     __syncthreads();
     const int flags = consts->end_flags;
-    int *my_scratch = scratch + (size_t)blockIdx.x * ((size_t)scratch_b_len + (size_t)GEN_RING * scratch_rowlen);
+    int *my_scratch = scratch + (size_t)blockIdx.x * ((size_t)scratch_b_len + (size_t)((blockDim.x >> 5) + 1) * scratch_rowlen);
 
     for (;;) {
         __syncthreads();  // every warp is done with the previous family (and has read sy.q)
@@ -611,7 +633,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32, 16 / GEN_WARPS) dp_general_ker
         if (q >= (unsigned)n_fams) break;
         const FamDesc f = fams[order ? order[q] : (int)q];
         const int n1 = f.n_fl + f.n_tr + f.n_fr;
-        const int R = strk_pick_rows(n1);
+        const int R = strk_pick_rows(n1, (int)(blockDim.x >> 5));
 #define STRK_CASE(RR)                                                                                          \
     case RR:                                                                                                   \
         if (REF)                                                                                               \

@@ -90,6 +90,9 @@ __host__ __device__ inline int strk_pick_rows(int n1, int warps = 4) {
     // Several strips (pipelined over the warps of a CTA): R = 16.  A cost model that trades rounds of the pipeline
     // against the step length (e.g. 11 strips of 384 rows instead of 9 of 512 for a 4 140-row window) was measured on
     // config 4 and lost 8 %: every additional strip adds its own hand-over lag and synchronisation.
+    // (Also measured, for the latency shape of api.cu -- more warps per CTA when a launch holds few reads: the smallest R
+    // with 32 * R * warps >= n1, all strips of a read in one round.  Slower at 12 and 16 warps than R = 16: every strip
+    // adds ~20 instructions of bookkeeping per step, and one read is bound by the issue slots of its SM.)
     (void)warps;
     return 16;
 }
