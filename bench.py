@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE.json config (2 = the headline)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: ONE 1M-locus catalog partitioned over the ranks by DP area, results gathered on rank 0")
+    ap.add_argument("--strong-sub-blocks", type=int, default=0,
+                    help="--scaling strong: stream a partition in blocks of about 1/N of it (0 = the catalog's own blocks)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = the same number of blocks as --steps")
     ap.add_argument("--loci3", type=int, default=100_000, help="--config 3: loci in the config")
     return ap.parse_args()
@@ -377,10 +379,14 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
     bounds = sharding.partition_catalog(cost, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     # pass 2: the blocks of my partition, as host arrays (nibble-packed, pinned) + their reference windows
-    # The partition is streamed in blocks of at most `block` loci and about a twelfth of the partition: the first
-    # block's copy and the last block's download are the part of the stream that nothing overlaps, so a rank with a
-    # small partition (N = 8: 131 072 loci) takes smaller blocks.
-    sub = int(min(block, max(4096, -(-((hi - lo) // 12) // 1024) * 1024)))
+    # The partition is streamed in the catalog's own blocks (32 768 loci).  --strong-sub-blocks K: blocks of about 1 / K
+    # of the partition instead -- the first block's copy and the last block's download are the part of the stream that
+    # nothing overlaps, so smaller blocks should help a rank with a small partition.  Measured with K = 12: N = 4
+    # unchanged (213.4 M), N = 8 202.7 M with ONE rank at 155 ms and seven at 71-76 ms (whole blocks: 397.4 M, every rank
+    # at 74-78 ms); not re-measured, so the proven layout stays the default.
+    sub_block = block
+    if args.strong_sub_blocks > 0:
+        sub_block = int(min(block, max(4096, -(-((hi - lo) // args.strong_sub_blocks) // 1024) * 1024)))
     mine, refs = [], []
     for i in range(n_blocks):
         b_lo, b_hi = max(lo, i * block), min(hi, (i + 1) * block)
@@ -389,8 +395,8 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
         sb_ = synth.generate(synth.CONFIGS[2], block, seed=batch_seed(0, i), device=str(dev), chunk_loci=4096)
         whole = sb_.to_host()
         del sb_
-        for s0 in range(b_lo, b_hi, sub):
-            ha = whole.slice_loci(s0 - i * block, min(s0 + sub, b_hi) - i * block, compact=True)
+        for s0 in range(b_lo, b_hi, sub_block):
+            ha = whole.slice_loci(s0 - i * block, min(s0 + sub_block, b_hi) - i * block, compact=True)
             hb = ha.to_nibble()
             for a in (hb.arena, hb.seq_off, hb.lens, hb.est_cn, hb.read_begin, hb.motif_off, hb.motif_len):
                 register(a)
@@ -433,7 +439,7 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
     # warm both contexts and grow their recycled device buffers to the LARGEST block of the partition (a partition
     # that starts inside a block begins with a short one: growing the buffers later would put cudaMalloc / cudaFree,
     # which synchronise the device, inside the timed region)
-    big = max(range(len(mine)), key=lambda i: mine[i].n_reads) if mine else 0
+    big = max(range(len(mine)), key=lambda i: (mine[i].n_reads, mine[i].arena.nbytes)) if mine else 0
     for w in range(max(1, args.warmup)):
         for _ in eng.count_reads_stream([mine[big], mine[big]], params, outs=[outs[big], outs[big]], refs=[refs[big], refs[big]]):
             pass
@@ -485,7 +491,7 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
                         "h2d_bytes_per_step": int(sum(b.nbytes() for b in mine) / max(1, len(mine))),
                         "d2h_bytes_per_step": int(sum(o.nbytes for o in outs) / max(1, len(outs)))},
                 "partition": {"loci_per_rank": [int(bounds[r + 1] - bounds[r]) for r in range(world)],
-                              "loci_per_streamed_block": sub,
+                              "loci_per_streamed_block": sub_block,
                               "compute_s_per_rank": per_rank, "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
                               "gather_s": t_total - max(per_rank), "total_s": t_total,
                               "gather": "per-block D2H straight into one shared-memory result array; closing barrier"},
