@@ -155,6 +155,42 @@ def test_count_reads_stream_matches_blocking_calls_and_oracle(sb, oracle):
     eng.close()
 
 
+def test_small_pinned_batch_owns_nothing_after_upload_and_runs_on_a_foreign_stream(sb, oracle):
+    """include/strkit_b200.h: the library keeps no host pointer after a call returns.  A block of <= 512 reads (planned
+    on the host, copies queued asynchronously from PINNED arrays) is uploaded, every host array is overwritten at once,
+    and the batch runs on a stream the library does not own: results must be those of the arrays as uploaded."""
+    import torch
+
+    from strkit_b200 import synth
+    from strkit_b200.batcher import ReadBatch
+
+    params = sb.RepeatCountParams("repalign", 50, 3, 1)
+    eng = sb.Engine()
+    foreign = torch.cuda.Stream()
+    for seed, n_loci, nibble in ((3, 12, False), (4, 16, True), (5, 1, False)):
+        b = synth.generate(synth.CONFIGS[1], n_loci, seed=900 + seed).to_host(pin=True, nibble=nibble)
+        assert 0 < b.n_reads <= 512
+        keep = ReadBatch(arena=b.arena.copy(), seq_off=b.seq_off.copy(), lens=b.lens.copy(), est_cn=b.est_cn.copy(),
+                         read_begin=b.read_begin.copy(), motif_off=b.motif_off.copy(), motif_len=b.motif_len.copy(),
+                         arena_format=b.arena_format)
+        db = eng.upload(b)
+        b.arena[:] = 0x58 if not nibble else 0xFF  # the caller reuses its buffers straight away
+        b.seq_off[:] = 0
+        b.lens[:] = 1
+        b.est_cn[:] = 0
+        b.motif_off[:] = 0
+        b.motif_len[:] = 1
+        with torch.cuda.stream(foreign):
+            eng.run(db, params, stream=foreign.cuda_stream)
+        foreign.synchronize()
+        got = eng.download(db)
+        db.free()
+        a = keep.to_ascii() if nibble else keep
+        want, _ = oracle.count_loci(a.arena, a.seq_off, a.lens, a.est_cn, a.read_begin, a.motif_off, a.motif_len, n_threads=4)
+        assert np.array_equal(got, want)
+    eng.close()
+
+
 def test_batch_noisy_ont_and_bad_estimates_force_widening(sb, oracle):
     """Config-3-like reads with start estimates far off: the search leaves the first table window and
     the widening passes must still reproduce the reference trajectory exactly."""
