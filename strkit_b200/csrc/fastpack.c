@@ -4,13 +4,23 @@
  *   pack(loci, nibble=0, threads=0) -> (arena, seq_off, lens, est_cn, read_begin, motif_off, motif_len)   all bytearray
  *
  * `loci` is a sequence of objects with the attributes of batcher.LocusReads (motif, est_cn, tr_seqs,
- * flank_left_seqs, flank_right_seqs); sequences are ASCII str or bytes.  Pass 1 (under the GIL) walks the Python
- * objects once and records raw pointers, lengths and offsets; pass 2 (GIL released, `threads` pthreads over ranges of
- * reads, 0 = one per core up to 16) moves the bytes -- a plain copy, or the nibble encoding of
- * batcher.ARENA_NIBBLE (two symbols per byte, low nibble first, code = index into "ACGTRYSWKMBDHVNX"; every read and
- * motif starts on a byte boundary, so threads never share a byte).  A byte outside the alphabet has no nibble code:
- * ValueError, and pack_loci falls back to the ASCII layout.  Layout = the one documented in batcher.ReadBatch: per
- * read fl + tr + fr contiguous at seq_off[r] (in symbols), motifs after all reads.  Host-side plumbing only.
+ * flank_left_seqs, flank_right_seqs); sequences are ASCII str or bytes.
+ *   pass 0 (under the GIL): per LOCUS, fetch the five attributes and take references to the sequences; per read, the
+ *           start estimate (small ints: interpreter singletons, cache-resident).
+ *   pass 1 (GIL released, `threads` pthreads over ranges of loci balanced by reads; 0 = one per core up to 16):
+ *           A. every thread measures the three strings of each of its reads (lens[], per-thread symbol totals);
+ *           B. with the totals prefixed into arena offsets, every thread writes seq_off[] and moves the bytes --
+ *              a plain copy, or the nibble encoding of batcher.ARENA_NIBBLE (two symbols per byte, low nibble first,
+ *              code = index into "ACGTRYSWKMBDHVNX"; every read and motif starts on a byte boundary, so threads never
+ *              share a byte).
+ *           The walk over the str objects is the expensive part (each is its own heap object: three cache misses per
+ *           read), so it is the part that is threaded.  The threads only READ immutable objects (type, length, the
+ *           inline character data of a compact ASCII str / of a bytes) that pass 0 keeps alive through the lists that
+ *           hold them; they take no references and call no API that can raise.  As with any buffer handed to a
+ *           GIL-free section, the caller must not mutate the lists while the call runs.
+ * A byte outside the alphabet has no nibble code: ValueError, and pack_loci falls back to the ASCII layout.  Layout =
+ * the one documented in batcher.ReadBatch: per read fl + tr + fr contiguous at seq_off[r] (in symbols), motifs after
+ * all reads.  Host-side plumbing only.
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
@@ -19,47 +29,41 @@
 #include <string.h>
 #include <unistd.h>
 
-/* ASCII str or bytes -> (pointer, length) */
-static int seq_view(PyObject *s, const char **p, Py_ssize_t *len) {
+/* ASCII str or bytes -> (pointer, length); no Python API that can raise or allocate: usable without the GIL.
+ * returns 0 ok, 1 not ASCII, 2 not str / bytes, 3 too long */
+static inline int seq_view_nogil(PyObject *s, const char **p, Py_ssize_t *len) {
     if (PyUnicode_Check(s)) {
-        if (!PyUnicode_IS_ASCII(s)) {
-            PyErr_SetString(PyExc_ValueError, "pack_loci: sequences must be ASCII");
-            return -1;
-        }
+        if (!PyUnicode_IS_ASCII(s)) return 1;
         *p = (const char *)PyUnicode_1BYTE_DATA(s);
         *len = PyUnicode_GET_LENGTH(s);
-        return 0;
-    }
-    if (PyBytes_Check(s)) {
+    } else if (PyBytes_Check(s)) {
         *p = PyBytes_AS_STRING(s);
         *len = PyBytes_GET_SIZE(s);
-        return 0;
+    } else {
+        return 2;
     }
-    PyErr_SetString(PyExc_TypeError, "pack_loci: sequences must be str or bytes");
-    return -1;
+    return *len > INT32_MAX ? 3 : 0;
 }
 
-static PyObject *fast_attr(PyObject *o, const char *name, const char *what) {
-    PyObject *a = PyObject_GetAttrString(o, name);
+static void set_view_error(int code, const char *what) {
+    if (code == 1)
+        PyErr_Format(PyExc_ValueError, "pack_loci: %s must be ASCII", what);
+    else if (code == 2)
+        PyErr_Format(PyExc_TypeError, "pack_loci: %s must be str or bytes", what);
+    else
+        PyErr_Format(PyExc_OverflowError, "pack_loci: %s too long", what);
+}
+
+/* attribute names, interned once at module init (PyObject_GetAttrString builds a str per call) */
+static PyObject *g_names[5];
+
+static PyObject *fast_attr(PyObject *o, PyObject *name, const char *what) {
+    PyObject *a = PyObject_GetAttr(o, name);
     if (!a) return NULL;
     PyObject *f = PySequence_Fast(a, what);
     Py_DECREF(a);
     return f;
 }
-
-typedef struct {
-    const char *p;
-    int32_t len;
-    uint64_t off; /* symbol offset of the piece in the arena */
-} Piece;
-
-typedef struct {
-    const Piece *pieces;
-    Py_ssize_t begin, end; /* pieces [begin, end); a read's three pieces never straddle two jobs */
-    char *arena;
-    int nibble;
-    int bad; /* out: a byte without a nibble code was seen */
-} CopyJob;
 
 static unsigned char g_code[256];
 static void init_codes(void) {
@@ -71,38 +75,104 @@ static void init_codes(void) {
     }
 }
 
-static void *copy_worker(void *arg) {
-    CopyJob *jb = (CopyJob *)arg;
+/* one piece into the arena at symbol offset `at`; returns the OR of the nibble codes seen (bit 4 = no code) */
+static inline unsigned put_piece(char *arena, uint64_t at, const char *p, int32_t len, int nibble) {
+    if (!nibble) {
+        memcpy(arena + at, p, (size_t)len);
+        return 0;
+    }
+    const unsigned char *src = (const unsigned char *)p;
+    unsigned char *dst = (unsigned char *)arena;
     unsigned bad = 0;
-    for (Py_ssize_t k = jb->begin; k < jb->end; ++k) {
-        const Piece *pc = &jb->pieces[k];
-        if (!jb->nibble) {
-            memcpy(jb->arena + pc->off, pc->p, (size_t)pc->len);
-            continue;
-        }
-        const unsigned char *src = (const unsigned char *)pc->p;
-        unsigned char *dst = (unsigned char *)jb->arena;
-        uint64_t at = pc->off;
-        int32_t i = 0;
-        if ((at & 1) && pc->len > 0) { /* finish the byte the previous piece of this read started */
-            const unsigned c = g_code[src[0]];
-            bad |= c;
-            dst[at >> 1] |= (unsigned char)(c << 4);
-            ++at, ++i;
-        }
-        for (; i + 1 < pc->len; i += 2, at += 2) {
-            const unsigned c0 = g_code[src[i]], c1 = g_code[src[i + 1]];
-            bad |= c0 | c1;
-            dst[at >> 1] = (unsigned char)(c0 | (c1 << 4));
-        }
-        if (i < pc->len) {
-            const unsigned c = g_code[src[i]];
-            bad |= c;
-            dst[at >> 1] = (unsigned char)c;
+    int32_t i = 0;
+    if ((at & 1) && len > 0) { /* finish the byte the previous piece of this read started */
+        const unsigned c = g_code[src[0]];
+        bad |= c;
+        dst[at >> 1] |= (unsigned char)(c << 4);
+        ++at, ++i;
+    }
+    for (; i + 1 < len; i += 2, at += 2) {
+        const unsigned c0 = g_code[src[i]], c1 = g_code[src[i + 1]];
+        bad |= c0 | c1;
+        dst[at >> 1] = (unsigned char)(c0 | (c1 << 4));
+    }
+    if (i < len) {
+        const unsigned c = g_code[src[i]];
+        bad |= c;
+        dst[at >> 1] = (unsigned char)c;
+    }
+    return bad;
+}
+
+typedef struct {
+    PyObject **keep;      /* per locus: motif, est_cn, tr_seqs, flank_left_seqs, flank_right_seqs (sequences: fast) */
+    const int64_t *rbp;   /* read_begin */
+    Py_ssize_t l0, l1;    /* my loci */
+    int nibble, phase;    /* phase 0: measure, 1: place + copy */
+    int32_t *ln;          /* lens[3 * reads] */
+    uint64_t *so;         /* seq_off[reads] */
+    char *arena;
+    uint64_t base, total; /* symbols: my first offset (in), my total (out of phase 0) */
+    int err;              /* seq_view_nogil code of the first bad sequence, 0 = none */
+    int bad;              /* a byte without a nibble code was seen */
+} WalkJob;
+
+static void *walk_worker(void *arg) {
+    WalkJob *jb = (WalkJob *)arg;
+    uint64_t at = jb->phase ? jb->base : 0;
+    unsigned bad = 0;
+    for (Py_ssize_t i = jb->l0; i < jb->l1; ++i) {
+        PyObject **k = jb->keep + 5 * i;
+        const Py_ssize_t n = PySequence_Fast_GET_SIZE(k[2]);
+        PyObject **tr_items = PySequence_Fast_ITEMS(k[2]);
+        PyObject **fl_items = PySequence_Fast_ITEMS(k[3]), **fr_items = PySequence_Fast_ITEMS(k[4]);
+        Py_ssize_t r_glob = (Py_ssize_t)jb->rbp[i];
+        for (Py_ssize_t r = 0; r < n; ++r, ++r_glob) {
+            /* every str is its own heap object: the walk is bound by cache misses on the object headers, so the
+             * headers of a few reads ahead are prefetched while this one is handled */
+            if (r + 6 < n) {
+                __builtin_prefetch(fl_items[r + 6]);
+                __builtin_prefetch(tr_items[r + 6]);
+                __builtin_prefetch(fr_items[r + 6]);
+            }
+            PyObject *parts[3] = {fl_items[r], tr_items[r], fr_items[r]};
+            if (jb->phase) jb->so[r_glob] = at;
+            for (int q = 0; q < 3; ++q) {
+                const char *p = NULL;
+                Py_ssize_t len = 0;
+                const int e = seq_view_nogil(parts[q], &p, &len);
+                if (e) {
+                    if (!jb->err) jb->err = e;
+                    len = 0;
+                }
+                if (jb->phase)
+                    bad |= put_piece(jb->arena, at, p, (int32_t)len, jb->nibble);
+                else
+                    jb->ln[3 * r_glob + q] = (int32_t)len;
+                at += (uint64_t)len;
+            }
+            if (jb->nibble) at += at & 1; /* next read starts on a byte boundary */
         }
     }
+    if (!jb->phase) jb->total = at;
     jb->bad = (bad & 16u) != 0;
     return NULL;
+}
+
+static void run_jobs(WalkJob *jobs, int nt) {
+    pthread_t th[64];
+    if (nt == 1) {
+        walk_worker(&jobs[0]);
+        return;
+    }
+    int started = 0;
+    for (int t = 1; t < nt; ++t) { /* job 0 runs here */
+        if (pthread_create(&th[t], NULL, walk_worker, &jobs[t]) != 0) break;
+        ++started;
+    }
+    walk_worker(&jobs[0]);
+    for (int t = 1 + started; t < nt; ++t) walk_worker(&jobs[t]); /* could not spawn: do it here */
+    for (int t = 1; t <= started; ++t) pthread_join(th[t], NULL);
 }
 
 static PyObject *pack(PyObject *self, PyObject *args, PyObject *kwargs) {
@@ -116,21 +186,20 @@ static PyObject *pack(PyObject *self, PyObject *args, PyObject *kwargs) {
     const Py_ssize_t n_loci = PySequence_Fast_GET_SIZE(seq);
     PyObject **keep = (PyObject **)PyMem_Calloc((size_t)(5 * n_loci + 1), sizeof(PyObject *)); /* new references */
     PyObject *res = NULL, *arena = NULL, *seq_off = NULL, *lens = NULL, *est = NULL, *rb = NULL, *moff = NULL, *mlen = NULL;
-    Piece *pieces = NULL;
     if (!keep) {
         Py_DECREF(seq);
         return PyErr_NoMemory();
     }
-    /* count reads first (cheap), then one walk that fills everything but the arena */
+    /* pass 0a: attributes and read counts */
     Py_ssize_t n_reads = 0;
     for (Py_ssize_t i = 0; i < n_loci; ++i) {
         PyObject *lr = PySequence_Fast_GET_ITEM(seq, i);
         PyObject **k = keep + 5 * i;
-        if (!(k[0] = PyObject_GetAttrString(lr, "motif"))) goto fail;
-        if (!(k[1] = fast_attr(lr, "est_cn", "est_cn must be a sequence"))) goto fail;
-        if (!(k[2] = fast_attr(lr, "tr_seqs", "tr_seqs must be a sequence"))) goto fail;
-        if (!(k[3] = fast_attr(lr, "flank_left_seqs", "flank_left_seqs must be a sequence"))) goto fail;
-        if (!(k[4] = fast_attr(lr, "flank_right_seqs", "flank_right_seqs must be a sequence"))) goto fail;
+        if (!(k[0] = PyObject_GetAttr(lr, g_names[0]))) goto fail;
+        if (!(k[1] = fast_attr(lr, g_names[1], "est_cn must be a sequence"))) goto fail;
+        if (!(k[2] = fast_attr(lr, g_names[2], "tr_seqs must be a sequence"))) goto fail;
+        if (!(k[3] = fast_attr(lr, g_names[3], "flank_left_seqs must be a sequence"))) goto fail;
+        if (!(k[4] = fast_attr(lr, g_names[4], "flank_right_seqs must be a sequence"))) goto fail;
         const Py_ssize_t n = PySequence_Fast_GET_SIZE(k[2]);
         if (PySequence_Fast_GET_SIZE(k[1]) != n || PySequence_Fast_GET_SIZE(k[3]) != n || PySequence_Fast_GET_SIZE(k[4]) != n) {
             PyErr_SetString(PyExc_ValueError, "LocusReads: per-read sequences must have equal lengths");
@@ -144,12 +213,10 @@ static PyObject *pack(PyObject *self, PyObject *args, PyObject *kwargs) {
     rb = PyByteArray_FromStringAndSize(NULL, (n_loci + 1) * 8);
     moff = PyByteArray_FromStringAndSize(NULL, n_loci * 8);
     mlen = PyByteArray_FromStringAndSize(NULL, n_loci * 4);
-    pieces = (Piece *)PyMem_Malloc(sizeof(Piece) * (size_t)(3 * n_reads + n_loci + 1));
-    if (!seq_off || !lens || !est || !rb || !moff || !mlen || !pieces) {
+    if (!seq_off || !lens || !est || !rb || !moff || !mlen) {
         if (!PyErr_Occurred()) PyErr_NoMemory();
         goto fail;
     }
-    uint64_t at = 0; /* symbols */
     {
         uint64_t *so = (uint64_t *)PyByteArray_AS_STRING(seq_off);
         int32_t *ln = (int32_t *)PyByteArray_AS_STRING(lens);
@@ -157,22 +224,14 @@ static PyObject *pack(PyObject *self, PyObject *args, PyObject *kwargs) {
         int64_t *rbp = (int64_t *)PyByteArray_AS_STRING(rb);
         uint64_t *mo = (uint64_t *)PyByteArray_AS_STRING(moff);
         int32_t *ml = (int32_t *)PyByteArray_AS_STRING(mlen);
+        /* pass 0b: read_begin and the start estimates */
         Py_ssize_t r_glob = 0;
         rbp[0] = 0;
         for (Py_ssize_t i = 0; i < n_loci; ++i) {
             PyObject **k = keep + 5 * i;
-            const Py_ssize_t n = PySequence_Fast_GET_SIZE(k[2]);
-            PyObject **e_items = PySequence_Fast_ITEMS(k[1]), **tr_items = PySequence_Fast_ITEMS(k[2]);
-            PyObject **fl_items = PySequence_Fast_ITEMS(k[3]), **fr_items = PySequence_Fast_ITEMS(k[4]);
+            const Py_ssize_t n = PySequence_Fast_GET_SIZE(k[1]);
+            PyObject **e_items = PySequence_Fast_ITEMS(k[1]);
             for (Py_ssize_t r = 0; r < n; ++r, ++r_glob) {
-                /* every str is its own heap object: the walk is bound by cache misses on the object headers, so the
-                 * headers of a few reads ahead are prefetched while this one is recorded */
-                if (r + 6 < n) {
-                    __builtin_prefetch(fl_items[r + 6]);
-                    __builtin_prefetch(tr_items[r + 6]);
-                    __builtin_prefetch(fr_items[r + 6]);
-                    __builtin_prefetch(e_items[r + 6]);
-                }
                 const long e = PyLong_AsLong(e_items[r]);
                 if (e == -1 && PyErr_Occurred()) goto fail;
                 if (e < INT32_MIN || e > INT32_MAX) {
@@ -180,78 +239,71 @@ static PyObject *pack(PyObject *self, PyObject *args, PyObject *kwargs) {
                     goto fail;
                 }
                 ec[r_glob] = (int32_t)e;
-                so[r_glob] = at;
-                PyObject *parts[3] = {fl_items[r], tr_items[r], fr_items[r]};
-                for (int q = 0; q < 3; ++q) {
-                    const char *p;
-                    Py_ssize_t len;
-                    if (seq_view(parts[q], &p, &len)) goto fail;
-                    if (len > INT32_MAX) {
-                        PyErr_SetString(PyExc_OverflowError, "pack_loci: sequence too long");
-                        goto fail;
-                    }
-                    Piece *pc = &pieces[3 * r_glob + q];
-                    pc->p = p, pc->len = (int32_t)len, pc->off = at;
-                    ln[3 * r_glob + q] = (int32_t)len;
-                    at += (uint64_t)len;
-                }
-                if (nibble) at += at & 1; /* next read starts on a byte boundary */
             }
             rbp[i + 1] = (int64_t)r_glob;
         }
-        for (Py_ssize_t i = 0; i < n_loci; ++i) { /* motifs after all reads */
+        /* motifs: measured here, placed after all reads */
+        for (Py_ssize_t i = 0; i < n_loci; ++i) {
             const char *p;
             Py_ssize_t len;
-            if (seq_view(keep[5 * i], &p, &len)) goto fail;
-            if (len > INT32_MAX) {
-                PyErr_SetString(PyExc_OverflowError, "pack_loci: motif too long");
+            const int e = seq_view_nogil(keep[5 * i], &p, &len);
+            if (e) {
+                set_view_error(e, "motif");
                 goto fail;
             }
-            Piece *pc = &pieces[3 * n_reads + i];
-            pc->p = p, pc->len = (int32_t)len, pc->off = at;
-            mo[i] = at;
             ml[i] = (int32_t)len;
-            at += (uint64_t)len;
-            if (nibble) at += at & 1;
         }
-    }
-    arena = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)(nibble ? (at + 1) / 2 : at));
-    if (!arena) goto fail;
-    {
-        /* pass 2: move the bytes, GIL released (the str / bytes objects are kept alive by `keep` and `seq`) */
-        const Py_ssize_t n_pieces = 3 * n_reads + n_loci;
+        /* pass 1: ranges of loci with about equal numbers of reads */
         long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
         int nt = threads > 0 ? threads : (int)(ncpu < 1 ? 1 : (ncpu > 16 ? 16 : ncpu));
         if ((Py_ssize_t)nt > n_reads / 4096 + 1) nt = (int)(n_reads / 4096 + 1);
-        CopyJob jobs[64];
-        pthread_t th[64];
         if (nt > 64) nt = 64;
-        char *a = PyByteArray_AS_STRING(arena);
-        for (int t = 0; t < nt; ++t) {
-            const Py_ssize_t r0 = n_reads * t / nt, r1 = n_reads * (t + 1) / nt;
-            jobs[t].pieces = pieces;
-            jobs[t].begin = 3 * r0;
-            jobs[t].end = t == nt - 1 ? n_pieces : 3 * r1; /* the last job also takes the motifs */
-            jobs[t].arena = a;
-            jobs[t].nibble = nibble;
-            jobs[t].bad = 0;
-        }
-        int bad = 0;
-        Py_BEGIN_ALLOW_THREADS
-        if (nt == 1) {
-            copy_worker(&jobs[0]);
-        } else {
-            int started = 0;
+        WalkJob jobs[64];
+        {
+            Py_ssize_t i = 0;
             for (int t = 0; t < nt; ++t) {
-                if (pthread_create(&th[t], NULL, copy_worker, &jobs[t]) != 0) break;
-                ++started;
+                const int64_t want = (int64_t)n_reads * (t + 1) / nt;
+                jobs[t].l0 = i;
+                while (i < n_loci && (t == nt - 1 || rbp[i + 1] <= want)) ++i;
+                jobs[t].l1 = i;
+                jobs[t].keep = keep, jobs[t].rbp = rbp, jobs[t].nibble = nibble, jobs[t].phase = 0;
+                jobs[t].ln = ln, jobs[t].so = so, jobs[t].arena = NULL;
+                jobs[t].base = jobs[t].total = 0, jobs[t].err = 0, jobs[t].bad = 0;
             }
-            for (int t = started; t < nt; ++t) copy_worker(&jobs[t]); /* could not spawn: do it here */
-            for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+        }
+        Py_BEGIN_ALLOW_THREADS
+        run_jobs(jobs, nt);
+        Py_END_ALLOW_THREADS
+        uint64_t at = 0; /* symbols */
+        for (int t = 0; t < nt; ++t) {
+            if (jobs[t].err) {
+                set_view_error(jobs[t].err, "sequences");
+                goto fail;
+            }
+            jobs[t].base = at;
+            at += jobs[t].total; /* (a thread's total ends on a byte boundary in the nibble layout) */
+        }
+        for (Py_ssize_t i = 0; i < n_loci; ++i) { /* motifs after all reads */
+            mo[i] = at;
+            at += (uint64_t)ml[i];
+            if (nibble) at += at & 1;
+        }
+        arena = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)(nibble ? (at + 1) / 2 : at));
+        if (!arena) goto fail;
+        char *a = PyByteArray_AS_STRING(arena);
+        for (int t = 0; t < nt; ++t) jobs[t].phase = 1, jobs[t].arena = a;
+        unsigned bad = 0;
+        Py_BEGIN_ALLOW_THREADS
+        run_jobs(jobs, nt);
+        for (Py_ssize_t i = 0; i < n_loci; ++i) {
+            const char *p = NULL;
+            Py_ssize_t len = 0;
+            seq_view_nogil(keep[5 * i], &p, &len);
+            bad |= put_piece(a, mo[i], p, (int32_t)len, nibble);
         }
         Py_END_ALLOW_THREADS
-        for (int t = 0; t < nt; ++t) bad |= jobs[t].bad;
-        if (bad) {
+        for (int t = 0; t < nt; ++t) bad |= jobs[t].bad ? 16u : 0u;
+        if (bad & 16u) {
             PyErr_SetString(PyExc_ValueError, "pack_loci: a byte outside ACGTRYSWKMBDHVNX has no nibble code");
             goto fail;
         }
@@ -265,7 +317,6 @@ fail:
     Py_XDECREF(rb);
     Py_XDECREF(moff);
     Py_XDECREF(mlen);
-    PyMem_Free(pieces);
     for (Py_ssize_t i = 0; i < 5 * n_loci; ++i) Py_XDECREF(keep[i]);
     PyMem_Free(keep);
     Py_DECREF(seq);
@@ -278,6 +329,9 @@ static PyMethodDef methods[] = {{"pack", (PyCFunction)(void (*)(void))pack, METH
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_fastpack", "C helper of strkit_b200.batcher.pack_loci", -1, methods,
                                     NULL, NULL, NULL, NULL};
 PyMODINIT_FUNC PyInit__fastpack(void) {
+    static const char *names[5] = {"motif", "est_cn", "tr_seqs", "flank_left_seqs", "flank_right_seqs"};
     init_codes();
+    for (int i = 0; i < 5; ++i)
+        if (!(g_names[i] = PyUnicode_InternFromString(names[i]))) return NULL;
     return PyModule_Create(&moddef);
 }

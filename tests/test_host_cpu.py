@@ -243,6 +243,53 @@ def test_pack_loci_layouts_agree():
         pack_loci([LocusReads("CAG", [3], ["CAG-AG"], ["AC"], ["GT"])]).to_nibble()
 
 
+def test_pack_loci_threaded_walk_equals_single_thread():
+    """Enough reads that the helper really splits the walk over its threads (one per 4 096 reads at most): ranges of
+    loci of uneven size, every output array identical to one thread and to the pure-Python body, both layouts; an
+    error found by a worker thread (non-ASCII str, wrong type, byte without a nibble code) surfaces as the exception
+    of the single-threaded path."""
+    from strkit_b200 import batcher
+    from strkit_b200.batcher import LocusReads, pack_loci
+
+    if batcher._fastpack is None:
+        pytest.skip("_fastpack.so not built")
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def seq(n):
+        return letters[rng.integers(0, 4, n)].tobytes().decode()
+
+    loci = []
+    for l in range(700):
+        n = int(rng.integers(0, 60))
+        motif = seq(int(rng.integers(1, 7)))
+        loci.append(LocusReads(motif, [int(rng.integers(0, 50)) for _ in range(n)],
+                               [seq(int(rng.integers(0, 90))) for _ in range(n)], [seq(int(rng.integers(0, 12))) for _ in range(n)],
+                               [seq(int(rng.integers(0, 12))) for _ in range(n)]))
+    assert sum(len(x.tr_seqs) for x in loci) > 3 * 4096
+    for nibble in (False, True):
+        one = pack_loci(loci, nibble=nibble, threads=1)
+        body = pack_loci(loci, nibble=nibble, use_helper=False)
+        for threads in (2, 4, 7):
+            many = pack_loci(loci, nibble=nibble, threads=threads)
+            assert many.arena_format == one.arena_format == body.arena_format == int(nibble)
+            for f in ("arena", "seq_off", "lens", "est_cn", "read_begin", "motif_off", "motif_len"):
+                assert np.array_equal(getattr(many, f), getattr(one, f)), (f, threads, nibble)
+                if not nibble:  # (the Python body's nibble layout packs reads back to back: compared read by read above)
+                    assert np.array_equal(getattr(many, f), getattr(body, f)), (f, threads, nibble)
+        one.validate()
+    last = loci[-1]
+    bad_ascii = loci[:-1] + [LocusReads(last.motif, [1], ["AC\u00e9"], ["A"], ["C"])]
+    bad_type = loci[:-1] + [LocusReads(last.motif, [1], [17], ["A"], ["C"])]
+    bad_code = loci[:-1] + [LocusReads(last.motif, [1], ["AC-T"], ["A"], ["C"])]
+    for threads in (1, 4):
+        with pytest.raises(ValueError):
+            pack_loci(bad_ascii, threads=threads)
+        with pytest.raises(TypeError):
+            pack_loci(bad_type, threads=threads)
+        assert pack_loci(bad_code, nibble=True, threads=threads).arena_format == 0  # falls back to the ASCII layout
+
+
 def test_synth_nibble_and_compact_slices():
     from strkit_b200 import synth
 
