@@ -348,6 +348,27 @@ def run_other_config(args):
     print(json.dumps(line), flush=True)
 
 
+def strong_scaling_line(args, world, n_blocks, block, total_reads, t_total, per_rank, loci_per_rank, sub_block, h2d_per_block,
+                        d2h_per_block, launches, parity_ok, clocks, numa_note):
+    """The JSON line of --scaling strong (plain numbers in, a json.dumps-able dict out: tested on the CPU)."""
+    cfg = config_dict(args, world)
+    cfg["parallelism"] = (f"ONE catalog of {n_blocks * block} loci cut into {world} contiguous partitions of equal "
+                          "estimated DP area; no collective on the data path, one gather of the results to rank 0")
+    cfg["host_affinity"] = numa_note
+    per_rank = [float(t) for t in per_rank]
+    return {"metric": METRIC, "value": total_reads / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_total / n_blocks * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u16x2/int32", "data": "synthetic", "config": cfg,
+            "value_is": "whole job, host buffers in -> gathered host results out (reads + reference windows)",
+            "e2e": {"value": total_reads / t_total, "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_block),
+                    "d2h_bytes_per_step": int(d2h_per_block)},
+            "partition": {"loci_per_rank": [int(x) for x in loci_per_rank], "loci_per_streamed_block": int(sub_block),
+                          "compute_s_per_rank": per_rank, "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
+                          "gather_s": t_total - max(per_rank), "total_s": t_total,
+                          "gather": "per-block D2H straight into one shared-memory result array; closing barrier"},
+            "gpu_launches": int(launches), "parity_sample_bit_exact": bool(parity_ok), "clocks": clocks}
+
+
 def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, numa_note):
     """--scaling strong: ONE catalog of steps x loci_per_step loci (default 32 x 32 768 = 1M loci x 30 reads), cut into
     `world` contiguous partitions of equal estimated DP area (sharding.partition_catalog); every rank streams its
@@ -479,23 +500,11 @@ def run_strong_scaling(args, world, rank, local_rank, dev, barrier, reduce_max, 
                                      sub.motif_len, n_threads=os.cpu_count() or 1)
             r0 = locus0 * READS_PER_LOCUS
             ok = ok and bool(np.array_equal(result[r0:r0 + sub.n_reads], want))
-        cfg = config_dict(args, world)
-        cfg["parallelism"] = (f"ONE catalog of {n_blocks * block} loci cut into {world} contiguous partitions of equal "
-                              "estimated DP area; no collective on the data path, one gather of the results to rank 0")
-        cfg["host_affinity"] = numa_note
-        line = {"metric": METRIC, "value": total_reads / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": t_total / n_blocks * 1e3, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "u16x2/int32", "data": "synthetic", "config": cfg,
-                "value_is": "whole job, host buffers in -> gathered host results out (reads + reference windows)",
-                "e2e": {"value": total_reads / t_total, "unit": UNIT,
-                        "h2d_bytes_per_step": int(sum(b.nbytes() for b in mine) / max(1, len(mine))),
-                        "d2h_bytes_per_step": int(sum(o.nbytes for o in outs) / max(1, len(outs)))},
-                "partition": {"loci_per_rank": [int(bounds[r + 1] - bounds[r]) for r in range(world)],
-                              "loci_per_streamed_block": sub_block,
-                              "compute_s_per_rank": per_rank, "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
-                              "gather_s": t_total - max(per_rank), "total_s": t_total,
-                              "gather": "per-block D2H straight into one shared-memory result array; closing barrier"},
-                "gpu_launches": int(eng.total_launches - launches0), "parity_sample_bit_exact": ok, "clocks": clocks}
+        line = strong_scaling_line(args, world, n_blocks, block, total_reads, t_total, per_rank,
+                                   [int(bounds[r + 1] - bounds[r]) for r in range(world)], sub_block,
+                                   int(sum(b.nbytes() for b in mine) / max(1, len(mine))),
+                                   int(sum(o.nbytes for o in outs) / max(1, len(outs))),
+                                   int(eng.total_launches - launches0), ok, clocks, numa_note)
         print(json.dumps(line), flush=True)
     for o in outs:
         strkit_b200._native.lib.strk_host_unregister(o.ctypes.data)

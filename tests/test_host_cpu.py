@@ -192,6 +192,30 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
+def test_bench_strong_scaling_line_is_json(monkeypatch):
+    """bench.py --scaling strong needs GPUs to run, but the line it prints is assembled by a pure function: numpy
+    scalars in (what the run produces), one json.dumps-able dict with the contract's keys out."""
+    import importlib
+    import json
+    import sys
+
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--steps", "32", "--warmup", "3", "--scaling", "strong"])
+    bench = importlib.import_module("bench")
+    args = bench.parse_args()
+    line = bench.strong_scaling_line(args, 2, 32, 32768, np.int64(32 * 32768 * 30), np.float64(0.27),
+                                     [np.float64(0.26), np.float64(0.27)], [np.int64(524165), np.int64(524411)], np.int64(32768),
+                                     np.int64(86_000_000), np.int64(15_700_000), np.int64(828), np.bool_(True),
+                                     {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []}, None)
+    d = json.loads(json.dumps(line))
+    assert d["scaling"] == "strong" and d["n_gpus"] == 2 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] == d["e2e"]["value"] == pytest.approx(32 * 32768 * 30 / 0.27)
+    assert d["partition"]["loci_per_rank"] == [524165, 524411] and d["partition"]["loci_per_streamed_block"] == 32768
+    assert d["partition"]["imbalance_max_over_mean"] == pytest.approx(0.27 / 0.265)
+    for key in ("metric", "unit", "steps", "warmup", "ms_per_step", "dtype", "data", "config", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert "workload" in d["config"]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # host batcher: nibble arenas, compact slices, the C packing helper
 # ---------------------------------------------------------------------------------------------------------------
